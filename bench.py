@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- MCMC iterations/s of the SPOM engine on the shapes BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|tiny] [--impl ours|reference]
+
+A "step" is one MCMC iteration (sweep) of every chain resident on the GPU: refresh of the
+connectivity S, Metropolis steps on (alpha, b) and c, Gibbs updates of the latent z cells and of
+every free intermediate-state cell y (rank-1 updates of S), Metropolis steps on e (and p).
+metric = chain-iterations per second = (chains on all ranks) x K / (max over ranks of the device
+time of the K steps).  Default workload: cfg3 = synthetic N=10,000 patches x T=20 years, 8 chains
+per GPU (64 chains on 8 GPUs, weak scaling).  Under torchrun each rank owns its own block of
+chains (no data-path collective); NCCL is used only to gather the draws for R-hat.
+
+--impl reference times the CPU side (the reference's algorithm cannot run at N >= 32, so this is
+the FP64 C restatement of its per-cell terms in oracle/, one chain per host core, on a bounded
+sample of the same sweep) and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "mcmc_chain_iterations_per_sec"
+UNIT = "chain-iterations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def sampler_kwargs(wl):
+    c0 = wl["truth"]["c"]
+    return dict(sample_e=1, sample_c=1, sample_alpha=1, sample_b=1, sample_p=int(wl["detect"]),
+                e_min=0.0, e_max=1.0, c_min=0.0, c_max=20.0 * c0, alpha_min=1e-4, alpha_max=1e-1, b_min=0.0, b_max=2.0,
+                p_min=0.0, p_max=1.0, n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1)
+
+
+def start_params(wl):
+    t = wl["truth"]
+    return dict(e=0.5, c=t["c"], alpha=t["alpha"], b=t["b"], p=t["p"], K=1.0, Ksrc=0.0, dsrc=0.0)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- CPU side (oracle port)
+def cpu_sample(wl, chains, budget_s, steps=1, warmup=0):
+    """Time the oracle's sweep (FP64 C restatement, one chain per core) on a bounded sample:
+    the fixed part of a sweep (two full connectivity evaluations + parameter updates) in full,
+    the y scan on `limit` candidate cells per year, extrapolated to all candidates."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    m = O.Model(wl["obs"], geom=O.GEOM_COORDS, px=wl["px"], py=wl["py"], area=wl["area"], detect=wl["detect"])
+    cfg = O.sampler_cfg(**sampler_kwargs(wl))
+    sp = start_params(wl)
+    cores = O.lib().spom_max_threads()
+    nch = max(1, min(chains, cores))
+    ch = O.Chains(m, cfg, nch, seed=1000, par0=O.params(**sp), disperse=False)
+    ncand = int(((ch.z[0][:-1] & ch.z[0][1:]) == 1).sum())          # candidate cells per chain-sweep
+    # probe with 1 candidate per year to size the sample, then the measured sweeps
+    ch.run(1, y_flip_limit=1, nthreads=cores)
+    t_fixed0 = float(ch.phase_s[:, 0].max())
+    per_flip = max(float(ch.phase_s[:, 1].max()) / max(1.0, ch.visited / nch), 1e-7)   # s per candidate (one chain, one core)
+    per_sweep_budget = budget_s / max(1, steps + warmup)
+    per_year = int((per_sweep_budget - t_fixed0) / (per_flip * (wl["T"] - 1))) if per_sweep_budget > t_fixed0 else 1
+    per_year = int(min(max(per_year, 1), wl["n"]))
+    fixed, yscan, visited = [], [], []
+    for s in range(warmup + steps):
+        ch.run(1, y_flip_limit=per_year, nthreads=cores)
+        if s >= warmup:
+            fixed.append(float(ch.phase_s[:, 0].max())); yscan.append(float(ch.phase_s[:, 1].max())); visited.append(ch.visited / nch)
+    t_fixed, t_y, vis = float(np.mean(fixed)), float(np.mean(yscan)), float(np.mean(visited))
+    t_step = t_fixed + t_y
+    t_full = t_fixed + t_y * (ncand / max(vis, 1.0))                  # one sweep of nch chains, one per thread
+    value = nch / t_full                                              # chain-iterations/s with all cores busy
+    sample = (f"{nch} chains on {cores} threads, FP64 oracle port (CPU restatement of the reference's per-cell terms, "
+              f"not MIDASPOM_MPI.out: the reference enumerates 2^N states); per sweep: full connectivity refresh + "
+              f"proposal evaluated in full ({t_fixed:.2f} s), y scan timed on {int(vis)} of {ncand} candidate cells per chain "
+              f"({t_y:.3f} s) and extrapolated linearly to all of them")
+    return dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample, t_fixed_s=t_fixed, t_step_s=t_step,
+                ms_per_step=t_full * 1e3, measured_steps=len(fixed))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from midaspom_b200 import synth
+    wl = synth.make_workload(args.workload)
+    chains = wl["chains_per_gpu"] * max(1, args.gpus)
+    r = cpu_sample(wl, chains, args.cpu_seconds * 3, steps=args.steps, warmup=min(args.warmup, 1))
+    line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"{args.workload}: {wl['desc']}", n_patches=wl["n"], n_years=wl["T"], chains=chains,
+                            geometry="planar coordinates + areas"),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import midaspom_b200 as mb
+    from midaspom_b200 import synth, distributed as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = synth.make_workload(args.workload)
+    cpg = wl["chains_per_gpu"]
+    first, _ = D.chain_block(rank, world, cpg)
+    K, W = args.steps, args.warmup
+    n, T = wl["n"], wl["T"]
+    eng = mb.Engine(n, T, cpg, precision=mb.FP32, device=local_rank, seed=1000, detect=wl["detect"], chain_offset=first,
+                    max_draws=2 * K + W + 8)
+    eng.set_landscape_coords(wl["px"], wl["py"], wl["area"])
+    eng.set_source_units(None)
+    obs_pinned = torch.from_numpy(wl["obs"].copy()).pin_memory()
+    obs_host = obs_pinned.numpy()
+    eng.set_observations(obs_host)
+    eng.set_params([start_params(wl)] * cpg)
+    eng.init_chains(mb.engine.sampler_config(**sampler_kwargs(wl)), disperse=False)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(nsteps, e2e=False):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        draws = np.zeros((1, cpg, mb.NDRAW))
+        with torch.cuda.stream(stream):
+            for a, b in evs:
+                flush.fill_(1)                                   # evict the chain state from L2 between steps
+                a.record(stream)
+                if e2e:
+                    eng.set_observations(obs_host)               # H2D from pinned memory, every step
+                    eng.sweep(1, sync=False)
+                    draws = eng.get_draws(eng.num_draws() - 1, 1)  # D2H of the step's result (syncs)
+                else:
+                    eng.sweep(1, sync=False)
+                b.record(stream)
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs], draws
+
+    eng.sweep(W)                                                 # warm-up (untimed)
+    barrier()
+    eng.set_timing(True)
+    eng.get_timing(reset=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        step_ms, _ = timed_steps(K)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    kms, klaunch = eng.get_timing(reset=True)
+    eng.set_timing(False)
+    total_ms = float(sum(step_ms))
+    # end-to-end arm: host buffers in and out every step
+    barrier()
+    e2e_ms, last = timed_steps(K, e2e=True)
+    barrier()
+    e2e_total = float(sum(e2e_ms))
+    t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total = float(t[0]), float(t[1])
+    chains_total = cpg * world
+    value = chains_total * K / (total_ms * 1e-3)
+    e2e_value = chains_total * K / (e2e_total * 1e-3)
+
+    # posterior diagnostics on everything recorded so far (gathered over ranks with NCCL)
+    nd = eng.num_draws()
+    d_local = torch.from_numpy(eng.get_draws(0, nd)).to(f"cuda:{local_rank}")
+    d_all = D.gather_draws(d_local).cpu().numpy()
+    summ = D.posterior_summary(d_all[W:])
+    ess_min = min((v["ess"] for v in summ.values()), default=float("nan"))
+    run_s = (total_ms + e2e_total) * 1e-3
+
+    if rank == 0:
+        z, y = eng.get_state()
+        ncand = float(((z[:, :-1] & z[:, 1:]) == 1).sum()) / cpg             # candidate cells per chain-sweep
+        peaks_meas = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        hbm_peak = float(peaks_meas.get("hbm_gbs", 6650.0))
+        probe = eng.probe_peaks()
+        n_sweepy = max(1, klaunch["sweep_y"])
+        t_sweepy = kms["sweep_y"] / n_sweepy * 1e-3                           # s per launch (CUDA events, engine stream)
+        pairs = cpg * ncand * (n - 1)                                         # pair evaluations per launch
+        mufu_per_pair = 3                                                     # sqrt + ex2 + lg2 (planar geometry)
+        alg_bytes = cpg * (T - 1) * n * (8 + 1 + 1 + 1 + 8 + 1)               # read S,y,z_t,z_t+1 ; write S,y
+        t_conn = kms["conn"] / max(1, klaunch["conn"]) * 1e-3
+        conn_pairs = cpg * 2 * float(n) * n                                   # current + proposal parameter sets
+        roof = dict(bound="sfu", kernel="k_sweep_y", achieved=pairs * mufu_per_pair / t_sweepy * 1e-9,
+                    peak=probe["mufu_gops"], unit="Gop/s (MUFU)", frac=pairs * mufu_per_pair / t_sweepy * 1e-9 / probe["mufu_gops"],
+                    traffic=None, share_of_step=kms["sweep_y"] / max(total_ms, 1e-9), ms_per_launch=t_sweepy * 1e3,
+                    peak_source="mp_probe_peaks micro-benchmark on this GPU (MEASURED_PEAKS.json has no MUFU figure)",
+                    hbm=dict(achieved=alg_bytes / t_sweepy * 1e-9, peak=hbm_peak, unit="GB/s", frac=alg_bytes / t_sweepy * 1e-9 / hbm_peak,
+                             peak_source="MEASURED_PEAKS.json" if peaks_meas else "fallback"),
+                    conn=dict(kernel="k_conn", ms_per_launch=t_conn * 1e3, achieved=conn_pairs * 2 / t_conn * 1e-9,
+                              unit="Gop/s (MUFU)", frac=conn_pairs * 2 / t_conn * 1e-9 / probe["mufu_gops"],
+                              share_of_step=kms["conn"] / max(total_ms, 1e-9)),
+                    probe=probe)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms / K,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=f"{args.workload}: {wl['desc']}", n_patches=n, n_years=T, chains=chains_total,
+                                chains_per_gpu=cpg, geometry="planar coordinates + areas, on-the-fly weights",
+                                sampled=["e", "c", "alpha", "b"] + (["p"] if wl["detect"] else []),
+                                l2="flushed between timed steps (256 MiB write)", parallelism=f"chains x{world}"),
+                    clocks=clk.summary(),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(obs_host.nbytes),
+                             d2h_bytes_per_step=int(cpg * mb.NDRAW * 8), ms_per_step=e2e_total / K),
+                    gpu_launches=int(sum(klaunch.values())),
+                    kernel_ms={k: round(v, 4) for k, v in kms.items()}, kernel_launches=klaunch,
+                    wall_s_timed_region=t_wall,
+                    likelihood_evals_per_sec=chains_total * 2 * K / (total_ms * 1e-3),
+                    ess_per_sec=ess_min / run_s if run_s > 0 else None,
+                    posterior=summ, candidates_per_chain_sweep=ncand, roofline=roof)
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                r = cpu_sample(wl, cpg, args.cpu_seconds, steps=1, warmup=0)
+                line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+            except Exception as ex:  # the oracle is test infrastructure: never let it break the GPU line
+                line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="port", sample=f"failed: {ex}")
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

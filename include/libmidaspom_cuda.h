@@ -1,0 +1,149 @@
+/* libmidaspom_cuda.h -- C ABI of the B200-native SPOM likelihood / MCMC engine.
+ *
+ * This is the drop-in boundary for ONE hot path of nalcala/MIDASPOM: the stochastic patch
+ * occupancy model (SPOM) log-likelihood and its connectivity term.  The reference has no
+ * plugin/FFI boundary (each program is one C translation unit); the entry points below sit on its
+ * function-level seams and keep its conventions: plain C, caller-owned flat host arrays, years
+ * major / patches minor (piobs[i][j], main_MIDASPOM.c:152-161), scalars by value.  Unlike the
+ * reference they return an int status (0 = ok, <0 = error, text via mp_last_error) and never abort.
+ *
+ * Reference code each entry point replaces (paths under /root/reference/sources/):
+ *   mp_set_landscape_linear   main_MIDASPOM.c:177-188          kernel matrix M[i][j]=exp(-a|i-j|d) (flag -d);
+ *                             never materialised here: weights are evaluated on the fly
+ *   mp_set_landscape_coords / _dense                            (extension: general d_ij, areas A_j^b)
+ *   mp_set_observations       main_MIDASPOM.c:138-167           piobs table (-1/0/1), T x N
+ *   mp_connectivity           main_MIDASPOM.c:350-358           S_k = sum_{l!=k} M[l][k] y_l  (scalar triple loop)
+ *                             dieoff.c:73-79, loss.c:74-80,93-101, future.c:89-97
+ *   mp_loglik                 main_MIDASPOM.c:18-50 (compPePc), dieoff.c:51-83 (pije/pijc),
+ *                             loss.c:86-105 (pijcsource): the per-patch Bernoulli factors, summed as logs
+ *   mp_flip_delta             (no counterpart) rank-1 incremental form of the same terms
+ *   mp_sweep / mp_get_draws   replaces the (e,c) grid loops main_MIDASPOM.c:341-395 by data-augmented
+ *                             Gibbs/Metropolis chains; MIDASPOM_MPI's static row split
+ *                             (main_MIDASPOM_MPI.c:361-372,483-505) becomes chain sharding (chain_offset)
+ *   mp_set_era / mp_params.K,Ksrc,dsrc   dieoff.c:56-57,78 ; loss.c:93-101,365 ; future.c:67,90-97
+ *   mp_simulate               future.c:64-110 (simpij) + :359-386 (simulation loop)
+ *
+ * All device memory is owned by the engine handle; host buffers are owned by the caller.  One
+ * handle per GPU / host thread (thread-compatible, not thread-safe).  There is no CPU fallback:
+ * every entry point fails with MP_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef LIBMIDASPOM_CUDA_H
+#define LIBMIDASPOM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP_ABI_VERSION 1
+
+enum { MP_OK = 0, MP_ERR_ARG = -1, MP_ERR_CUDA = -2, MP_ERR_STATE = -3, MP_ERR_UNSUPPORTED = -4 };
+enum { MP_FP32 = 0, MP_FP64 = 1 };                       /* arithmetic of the weight / log terms */
+enum { MP_GEOM_LINEAR = 0, MP_GEOM_COORDS = 1, MP_GEOM_DENSE = 2 };
+
+#define MP_NDRAW 8   /* per (sweep, chain): e, c, alpha, b, p, loglik, #y=1, #z=1 */
+#define MP_NLSIG 5   /* log proposal scales: e, c, alpha, b, p */
+#define MP_NPART 4   /* loglik parts: extinction, colonisation, year-0 prior, detection */
+
+typedef struct mp_engine mp_engine;
+
+typedef struct {
+    int32_t  n_patches;      /* N */
+    int32_t  n_years;        /* T (rows of the observation table) */
+    int32_t  n_chains;       /* chains resident on this GPU */
+    int32_t  chain_offset;   /* global id of local chain 0 (RNG streams are keyed by global id) */
+    int32_t  precision;      /* MP_FP32 | MP_FP64 */
+    int32_t  device;         /* CUDA ordinal */
+    int32_t  detect;         /* 0: perfect detection (reference) ; 1: obs=0 hides z=1 w.p. 1-p */
+    int32_t  max_draws;      /* capacity (sweeps) of the device draw buffer */
+    uint64_t seed;
+    double   prior_occ;      /* flag -p: year-0 prior occupancy of latent cells (float in the reference) */
+} mp_config;
+
+/* e, c: flags/grid axes of the reference; alpha = 1/(flag -m); b: area exponent; p: detection;
+ * K: pre-event scaling (E=min(1,e/K), C=min(1,c*(K*S+...))); Ksrc, dsrc: external source size and
+ * distance unit (source term exp(-alpha*u_k*dsrc)*Ksrc, u_k = k+1 by default, loss.c:365). */
+typedef struct { double e, c, alpha, b, p, K, Ksrc, dsrc; } mp_params;
+
+typedef struct {
+    double  e_min, e_max, c_min, c_max, alpha_min, alpha_max, b_min, b_max, p_min, p_max;
+    int32_t sample_e, sample_c, sample_alpha, sample_b, sample_p;
+    int32_t n_e_steps, n_c_steps;   /* Metropolis sub-steps per sweep */
+    int32_t n_adapt;                /* sweeps during which proposal scales adapt */
+    int32_t update_z, update_y;     /* Gibbs updates of latent occupancy / intermediate state */
+} mp_sampler_config;
+
+/* kernel categories for mp_get_timing */
+enum { MP_K_CONN = 0, MP_K_COL = 1, MP_K_SWEEP_Y = 2, MP_K_SWEEP_Z = 3, MP_K_SMALL = 4, MP_K_SIM = 5, MP_K_NCAT = 6 };
+/* device buffers for mp_device_ptr (zero-copy hand-off to NCCL / torch) */
+enum { MP_BUF_DRAWS = 0, MP_BUF_Z = 1, MP_BUF_Y = 2, MP_BUF_S = 3, MP_BUF_PARAMS = 4 };
+
+const char *mp_version(void);
+int mp_device_count(void);
+
+int mp_create(const mp_config *cfg, mp_engine **out);
+int mp_destroy(mp_engine *h);
+const char *mp_last_error(const mp_engine *h);   /* h may be NULL: error of the last failed mp_create */
+
+/* ---- landscape (replaces the dense kernel matrix M) ---- */
+int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area /* N or NULL */);
+int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, const double *area);
+int mp_set_landscape_dense(mp_engine *h, const double *dist /* N*N, [source][target] */, const double *area);
+int mp_set_source_units(mp_engine *h, const double *src_unit /* N or NULL => k+1 */);
+
+/* ---- data ---- */
+int mp_set_observations(mp_engine *h, const int8_t *obs /* T*N, -1/0/1 */);
+int mp_set_era(mp_engine *h, const uint8_t *era /* T-1 flags or NULL */);
+
+/* ---- chain state ---- */
+int mp_set_params(mp_engine *h, const mp_params *par /* n_chains */);
+int mp_get_params(mp_engine *h, mp_params *par);
+int mp_set_state(mp_engine *h, const uint8_t *z /* C*T*N */, const uint8_t *y /* C*(T-1)*N */);
+int mp_get_state(mp_engine *h, uint8_t *z, uint8_t *y);
+int mp_set_scales(mp_engine *h, const double *lsig /* C*MP_NLSIG */);
+int mp_get_scales(mp_engine *h, double *lsig);
+
+/* ---- likelihood ---- */
+/* recompute S from the current y and parameters; S_out (host, C*(T-1)*N, nullable) */
+int mp_connectivity(mp_engine *h, double *S_out);
+int mp_get_connectivity(mp_engine *h, double *S_out);   /* copy of the resident S (no recompute) */
+/* complete-data log-likelihood per chain (recomputes S); parts: C*MP_NPART, nullable */
+int mp_loglik(mp_engine *h, double *ll, double *parts);
+/* one-call form: upload parameters and state, evaluate, download (host buffers in and out) */
+int mp_loglik_host(mp_engine *h, const mp_params *par, const uint8_t *z, const uint8_t *y, double *ll, double *parts);
+/* log-odds of flipping y[chain][t][k] by the rank-1 update of the resident S */
+int mp_flip_delta(mp_engine *h, int chain, int t, int k, double *dll);
+
+/* ---- sampler ---- */
+int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse);
+int mp_set_sampler(mp_engine *h, const mp_sampler_config *sc);
+int mp_sweep(mp_engine *h, int nsweeps);            /* asynchronous on the engine stream */
+int mp_synchronize(mp_engine *h);
+int mp_num_draws(mp_engine *h);
+int mp_get_draws(mp_engine *h, int first, int count, double *out /* count*C*MP_NDRAW */);
+int mp_reset_draws(mp_engine *h);
+int mp_sweep_index(mp_engine *h);
+
+/* ---- forward simulator ---- */
+/* nsims independent trajectories of nyears from z0 (N bytes); era_all != 0 applies K/Ksrc every
+ * year (future.c).  z_out (nullable): nsims*(nyears+1)*N ; occupied_out (nullable): nsims*(nyears+1) counts */
+int mp_simulate(mp_engine *h, const mp_params *par, const uint8_t *z0, int nyears, int nsims, uint64_t seed,
+                int era_all, uint8_t *z_out, int32_t *occupied_out);
+
+/* ---- plumbing ---- */
+int mp_device_ptr(mp_engine *h, int which, void **ptr, size_t *bytes);
+/* the cudaStream_t every kernel of this engine is launched on (for CUDA-event timing by the caller) */
+int mp_get_stream(mp_engine *h, void **stream);
+int mp_set_timing(mp_engine *h, int enabled);
+/* accumulated since the last call with reset != 0: ms[MP_K_NCAT], launches[MP_K_NCAT] */
+int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset);
+/* micro-benchmarks on the engine's device: out[0] MUFU.EX2 Gop/s, out[1] FP32 FMA GFMA/s,
+ * out[2] FP64 add Gop/s, out[3] device copy GB/s (read+write) */
+int mp_probe_peaks(mp_engine *h, double *out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBMIDASPOM_CUDA_H */

@@ -1,0 +1,853 @@
+// mp_engine.cu -- host side of libmidaspom_cuda.so: the engine handle, device memory, kernel
+// launch sequences and the extern "C" entry points declared in include/libmidaspom_cuda.h.
+// No CPU fallback: without a usable sm_100 device every entry point returns MP_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mp_kernels.cuh"
+
+using namespace mp;
+
+static thread_local std::string g_create_error;
+
+struct mp_engine {
+    mp_config cfg{};
+    mp_sampler_config sc{};
+    bool have_sc = false, have_landscape = false, have_obs = false, have_state = false;
+    int geom = MP_GEOM_LINEAR;
+    bool have_area = false;
+    double spacing = 100.0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // landscape
+    double *d_area = nullptr, *d_src_unit = nullptr;
+    void *d_px = nullptr, *d_py = nullptr, *d_dist = nullptr;   // float or double per cfg.precision
+    // data
+    int8_t *d_obs = nullptr;
+    uint8_t *d_era = nullptr;
+    bool have_era = false;
+    // chains
+    mp_params *d_par = nullptr, *d_prop = nullptr;
+    double *d_lsig = nullptr;
+    uint8_t *d_z = nullptr, *d_y = nullptr;
+    uint32_t *d_ybits = nullptr;
+    int nwords = 1;
+    double *d_S[2] = { nullptr, nullptr };
+    void *d_aw[2] = { nullptr, nullptr };
+    double *d_partial[2] = { nullptr, nullptr };
+    double *d_llc = nullptr, *d_logu = nullptr, *d_parts = nullptr, *d_scalar = nullptr;
+    int *d_flags = nullptr;
+    unsigned long long *d_counts = nullptr;
+    double *d_draws = nullptr;
+    int ndraws = 0;
+    uint32_t sweep = 0;
+    int nblk_col = 1;
+    // timing
+    bool timing = false;
+    struct Span { cudaEvent_t a, b; int cat; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    double t_ms[MP_K_NCAT] = { 0 };
+    long long t_launch[MP_K_NCAT] = { 0 };
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return MP_ERR_CUDA;                                                                          \
+        }                                                                                                \
+    } while (0)
+#define REQUIRE(cond, code, msg)                                                                         \
+    do { if (!(cond)) { h->err = (msg); return (code); } } while (0)
+
+static inline size_t nN(const mp_engine *h) { return (size_t)h->cfg.n_patches; }
+static inline size_t nT(const mp_engine *h) { return (size_t)h->cfg.n_years; }
+static inline size_t nC(const mp_engine *h) { return (size_t)h->cfg.n_chains; }
+static inline size_t zcells(const mp_engine *h) { return nT(h) * nN(h); }
+static inline size_t ycells(const mp_engine *h) { return (nT(h) - 1) * nN(h); }
+static inline bool is64(const mp_engine *h) { return h->cfg.precision == MP_FP64; }
+static inline size_t rsz(const mp_engine *h) { return is64(h) ? sizeof(double) : sizeof(float); }
+
+// ---- timing spans: CUDA events on the engine stream around every launch of a category
+struct Timed {
+    mp_engine *h; int cat; cudaEvent_t a = nullptr, b = nullptr;
+    Timed(mp_engine *h_, int cat_) : h(h_), cat(cat_)
+    {
+        h->t_launch[cat]++;
+        if (!h->timing) return;
+        a = take(); b = take();
+        cudaEventRecord(a, h->stream);
+    }
+    ~Timed()
+    {
+        if (!h->timing) return;
+        cudaEventRecord(b, h->stream);
+        h->spans.push_back({ a, b, cat });
+    }
+    cudaEvent_t take()
+    {
+        if (!h->pool.empty()) { cudaEvent_t e = h->pool.back(); h->pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+static void drain_spans(mp_engine *h)
+{
+    for (auto &s : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) h->t_ms[s.cat] += ms;
+        h->pool.push_back(s.a); h->pool.push_back(s.b);
+    }
+    h->spans.clear();
+}
+
+template <typename R> static Landscape<R> view(const mp_engine *h)
+{
+    Landscape<R> ls;
+    ls.n = h->cfg.n_patches; ls.spacing = (R)h->spacing;
+    ls.px = (const R *)h->d_px; ls.py = (const R *)h->d_py; ls.dist = (const R *)h->d_dist;
+    ls.src_unit = h->d_src_unit;
+    return ls;
+}
+static SamplerDev sampler_dev(const mp_engine *h)
+{
+    SamplerDev sd;
+    sd.sc = h->sc; sd.seed = h->cfg.seed; sd.chain_offset = h->cfg.chain_offset; sd.detect = h->cfg.detect;
+    sd.p0 = (double)(float)h->cfg.prior_occ;   // float in the reference (main_MIDASPOM.c:66,218)
+    return sd;
+}
+
+// ------------------------------------------------------------------ launch helpers
+template <typename R> static int launch_area_weights(mp_engine *h, int set)
+{
+    Timed tm(h, MP_K_SMALL);
+    const int n = h->cfg.n_patches;
+    dim3 grid((n + 255) / 256, h->cfg.n_chains);
+    k_area_weights<R><<<grid, 256, 0, h->stream>>>(set ? h->d_prop : h->d_par, h->have_area ? h->d_area : nullptr,
+                                                    (R *)h->d_aw[set], n);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+static int launch_pack_y(mp_engine *h)
+{
+    Timed tm(h, MP_K_SMALL);
+    const int n = h->cfg.n_patches;
+    dim3 grid((n + 255) / 256, h->cfg.n_chains);
+    k_pack_y<<<grid, 256, 0, h->stream>>>(h->d_y, h->d_ybits, n, h->cfg.n_years - 1, h->nwords);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int nsets)
+{
+    Timed tm(h, MP_K_CONN);
+    ConnArgs<R> a;
+    a.ls = view<R>(h);
+    a.par[0] = h->d_par; a.par[1] = h->d_prop;
+    a.aw[0] = (const R *)h->d_aw[0]; a.aw[1] = (const R *)h->d_aw[1];
+    a.S[0] = h->d_S[0]; a.S[1] = h->d_S[1];
+    a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords;
+    dim3 grid((h->cfg.n_patches + CONN_TILE - 1) / CONN_TILE, h->cfg.n_chains, nsets);
+    const int ny = a.ntrans;
+    if (ny <= 8) k_conn<R, GEOM, 8><<<grid, CONN_TILE, 0, h->stream>>>(a);
+    else if (ny <= 16) k_conn<R, GEOM, 16><<<grid, CONN_TILE, 0, h->stream>>>(a);
+    else if (ny <= 24) k_conn<R, GEOM, 24><<<grid, CONN_TILE, 0, h->stream>>>(a);
+    else k_conn<R, GEOM, 32><<<grid, CONN_TILE, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+template <typename R> static int launch_conn(mp_engine *h, int nsets)
+{
+    switch (h->geom) {
+    case MP_GEOM_LINEAR: return launch_conn_g<R, MP_GEOM_LINEAR>(h, nsets);
+    case MP_GEOM_COORDS: return launch_conn_g<R, MP_GEOM_COORDS>(h, nsets);
+    default: return launch_conn_g<R, MP_GEOM_DENSE>(h, nsets);
+    }
+}
+// colonisation log-likelihood partials: set s uses parameters par_s, connectivity S_s, writes partial[s]
+template <typename R>
+static int launch_col(mp_engine *h, int nsets, const mp_params *p0, const double *S0, const mp_params *p1, const double *S1)
+{
+    Timed tm(h, MP_K_COL);
+    ColArgs a;
+    a.par[0] = p0; a.par[1] = p1; a.S[0] = S0; a.S[1] = S1;
+    a.partial[0] = h->d_partial[0]; a.partial[1] = h->d_partial[1];
+    dim3 grid(h->nblk_col, h->cfg.n_chains, nsets);
+    k_col_ll<R><<<grid, COL_THREADS, 0, h->stream>>>(a, view<R>(h), h->d_z, h->d_y, h->have_era ? h->d_era : nullptr,
+                                                     h->cfg.n_years);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+static int launch_counts(mp_engine *h)
+{
+    Timed tm(h, MP_K_SMALL);
+    CK(cudaMemsetAsync(h->d_counts, 0, nC(h) * NCOUNT * sizeof(unsigned long long), h->stream));
+    const long long cells = (long long)zcells(h);
+    dim3 grid((unsigned)std::min<long long>((cells + 255) / 256, 1024), h->cfg.n_chains);
+    k_counts<<<grid, 256, 0, h->stream>>>(h->d_obs, h->have_era ? h->d_era : nullptr, h->d_z, h->d_y, h->d_counts,
+                                          h->cfg.n_patches, h->cfg.n_years, h->cfg.detect);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+template <typename R, int GEOM> static int launch_sweep_y_g(mp_engine *h)
+{
+    Timed tm(h, MP_K_SWEEP_Y);
+    constexpr int NT = sizeof(R) == 4 ? 1024 : 512;
+    const size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
+    auto kern = k_sweep_y<R, GEOM, NT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nthr = (int)std::min<size_t>(NT, ((nN(h) + 31) / 32) * 32);
+    kern<<<h->cfg.n_chains * (h->cfg.n_years - 1), nthr, smem, h->stream>>>(
+        sampler_dev(h), h->sweep, view<R>(h), h->d_par, (const R *)h->d_aw[0], h->have_era ? h->d_era : nullptr, h->d_z,
+        h->d_y, h->d_S[0], h->cfg.n_years);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+template <typename R> static int launch_sweep_y(mp_engine *h)
+{
+    const size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
+    REQUIRE(smem <= 227 * 1024, MP_ERR_UNSUPPORTED, "n_patches too large for the shared-memory resident y sweep");
+    switch (h->geom) {
+    case MP_GEOM_LINEAR: return launch_sweep_y_g<R, MP_GEOM_LINEAR>(h);
+    case MP_GEOM_COORDS: return launch_sweep_y_g<R, MP_GEOM_COORDS>(h);
+    default: return launch_sweep_y_g<R, MP_GEOM_DENSE>(h);
+    }
+}
+template <typename R> static int launch_update_z(mp_engine *h)
+{
+    Timed tm(h, MP_K_SWEEP_Z);
+    const long long cells = (long long)zcells(h);
+    dim3 grid((unsigned)std::min<long long>((cells + 255) / 256, 2048), h->cfg.n_chains);
+    k_update_z<R><<<grid, 256, 0, h->stream>>>(sampler_dev(h), h->sweep, view<R>(h), h->d_par, h->d_obs,
+                                               h->have_era ? h->d_era : nullptr, h->d_z, h->d_y, h->d_S[0], h->cfg.n_years);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+
+// recompute S (set 0) from the resident y and parameters
+template <typename R> static int refresh_S(mp_engine *h)
+{
+    int rc;
+    if ((rc = launch_pack_y(h)) != MP_OK) return rc;
+    if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
+    return launch_conn<R>(h, 1);
+}
+// per-chain complete-data log-likelihood of the resident state, using the resident S
+template <typename R> static int loglik_resident(mp_engine *h, double *d_draw_row, double *d_parts)
+{
+    int rc;
+    if ((rc = launch_counts(h)) != MP_OK) return rc;
+    if ((rc = launch_col<R>(h, 1, h->d_par, h->d_S[0], h->d_par, h->d_S[0])) != MP_OK) return rc;
+    Timed tm(h, MP_K_SMALL);
+    k_record<<<h->cfg.n_chains, 32, 0, h->stream>>>(sampler_dev(h), h->d_par, h->d_counts, h->d_partial[0], h->nblk_col,
+                                                    d_draw_row, d_parts);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+
+// one MCMC iteration of every resident chain
+template <typename R> static int sweep_once(mp_engine *h)
+{
+    int rc;
+    const int C = h->cfg.n_chains;
+    const SamplerDev sd = sampler_dev(h);
+    const bool do_ab = h->sc.sample_alpha || h->sc.sample_b;
+    const long long cells = (long long)ycells(h);
+    // A: refresh S, joint Metropolis step on (log alpha, b)
+    if ((rc = launch_pack_y(h)) != MP_OK) return rc;
+    if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
+    if (do_ab) {
+        { Timed tm(h, MP_K_SMALL);
+          k_propose_ab<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
+          CK(cudaGetLastError()); }
+        if ((rc = launch_area_weights<R>(h, 1)) != MP_OK) return rc;
+    }
+    if ((rc = launch_conn<R>(h, do_ab ? 2 : 1)) != MP_OK) return rc;
+    if ((rc = launch_col<R>(h, do_ab ? 2 : 1, h->d_par, h->d_S[0], h->d_prop, h->d_S[1])) != MP_OK) return rc;
+    { Timed tm(h, MP_K_SMALL);
+      k_decide_ab<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
+                                           h->d_partial[0], h->d_partial[1], h->nblk_col, h->d_llc, do_ab ? 1 : 0);
+      CK(cudaGetLastError()); }
+    if (do_ab) {
+        Timed tm(h, MP_K_SMALL);
+        dim3 grid((unsigned)std::min<long long>((cells + 255) / 256, 1024), C);
+        k_commit_ab<R><<<grid, 256, 0, h->stream>>>(h->d_flags, h->d_S[0], h->d_S[1], (R *)h->d_aw[0], (const R *)h->d_aw[1],
+                                                    cells, h->cfg.n_patches);
+        CK(cudaGetLastError());
+    }
+    // B: Metropolis steps on c (S unchanged)
+    if (h->sc.sample_c)
+        for (int s = 0; s < h->sc.n_c_steps; s++) {
+            { Timed tm(h, MP_K_SMALL);
+              k_propose_c<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, s, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
+              CK(cudaGetLastError()); }
+            // set 0 := the proposal => partial[0] holds the proposal's sums
+            if ((rc = launch_col<R>(h, 1, h->d_prop, h->d_S[0], h->d_prop, h->d_S[0])) != MP_OK) return rc;
+            Timed tm(h, MP_K_SMALL);
+            k_decide_c<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
+                                                h->d_partial[0], h->nblk_col, h->d_llc);
+            CK(cudaGetLastError());
+        }
+    // D: latent occupancy cells ; E: intermediate states
+    if (h->sc.update_z) if ((rc = launch_update_z<R>(h)) != MP_OK) return rc;
+    if (h->sc.update_y) if ((rc = launch_sweep_y<R>(h)) != MP_OK) return rc;
+    // C, F: e and p from the sufficient counts
+    if ((rc = launch_counts(h)) != MP_OK) return rc;
+    { Timed tm(h, MP_K_SMALL);
+      k_update_ep<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_lsig, h->d_counts, C);
+      CK(cudaGetLastError()); }
+    // record
+    if ((rc = launch_col<R>(h, 1, h->d_par, h->d_S[0], h->d_par, h->d_S[0])) != MP_OK) return rc;
+    {
+        Timed tm(h, MP_K_SMALL);
+        double *row = h->ndraws < h->cfg.max_draws ? h->d_draws + (size_t)h->ndraws * C * MP_NDRAW : nullptr;
+        k_record<<<C, 32, 0, h->stream>>>(sd, h->d_par, h->d_counts, h->d_partial[0], h->nblk_col, row, nullptr);
+        CK(cudaGetLastError());
+        if (row) h->ndraws++;
+    }
+    h->sweep++;
+    return MP_OK;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *mp_version(void) { return "midaspom_b200 0.1 (sm_100a, abi 1)"; }
+
+int mp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *mp_last_error(const mp_engine *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mp_destroy(mp_engine *h)
+{
+    if (!h) return MP_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drain_spans(h);
+    for (auto e : h->pool) cudaEventDestroy(e);
+    void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
+                     h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws };
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MP_OK;
+}
+
+int mp_create(const mp_config *cfg, mp_engine **out)
+{
+    if (!cfg || !out) { g_create_error = "mp_create: null argument"; return MP_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->n_patches < 1 || cfg->n_years < 2 || cfg->n_chains < 1 || cfg->max_draws < 0 ||
+        (cfg->precision != MP_FP32 && cfg->precision != MP_FP64)) {
+        g_create_error = "mp_create: need n_patches>=1, n_years>=2, n_chains>=1, precision MP_FP32|MP_FP64";
+        return MP_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("mp_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return MP_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "mp_create: bad device ordinal"; return MP_ERR_ARG; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MP_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "mp_create: device is not sm_100 (this library carries sm_100a code only)";
+        return MP_ERR_CUDA;
+    }
+    mp_engine *h = new mp_engine();
+    h->cfg = *cfg;
+    auto fail = [&](const char *what, cudaError_t ce) {
+        g_create_error = std::string("mp_create: ") + what + ": " + cudaGetErrorString(ce);
+        mp_destroy(h);
+        return MP_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    const size_t N = nN(h), T = nT(h), C = nC(h), R = rsz(h);
+    h->nwords = (int)((T - 1 + 31) / 32);
+    const long long cells = (long long)ycells(h);
+    h->nblk_col = (int)std::max<long long>(1, std::min<long long>(MAX_COL_BLOCKS, (cells + COL_THREADS * 8 - 1) / (COL_THREADS * 8)));
+    struct Req { void **p; size_t bytes; };
+    Req reqs[] = {
+        { (void **)&h->d_area, N * 8 }, { (void **)&h->d_src_unit, N * 8 }, { &h->d_px, N * R }, { &h->d_py, N * R },
+        { (void **)&h->d_obs, T * N }, { (void **)&h->d_era, T }, { (void **)&h->d_par, C * sizeof(mp_params) },
+        { (void **)&h->d_prop, C * sizeof(mp_params) }, { (void **)&h->d_lsig, C * MP_NLSIG * 8 },
+        { (void **)&h->d_z, C * T * N }, { (void **)&h->d_y, C * (T - 1) * N },
+        { (void **)&h->d_ybits, C * h->nwords * N * 4 }, { (void **)&h->d_S[0], C * (T - 1) * N * 8 },
+        { (void **)&h->d_S[1], C * (T - 1) * N * 8 }, { &h->d_aw[0], C * N * R }, { &h->d_aw[1], C * N * R },
+        { (void **)&h->d_partial[0], C * MAX_COL_BLOCKS * 8 }, { (void **)&h->d_partial[1], C * MAX_COL_BLOCKS * 8 },
+        { (void **)&h->d_llc, C * 8 }, { (void **)&h->d_logu, C * 8 }, { (void **)&h->d_parts, C * MP_NPART * 8 },
+        { (void **)&h->d_scalar, 64 }, { (void **)&h->d_flags, C * 4 * sizeof(int) },
+        { (void **)&h->d_counts, C * NCOUNT * sizeof(unsigned long long) },
+        { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
+    };
+    for (auto &r : reqs) {
+        if ((e = cudaMalloc(r.p, r.bytes)) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = cudaMemset(*r.p, 0, r.bytes)) != cudaSuccess) return fail("cudaMemset", e);
+    }
+    // defaults: parameters of the reference's defaults (main_MIDASPOM.c:66-73), neutral variant terms
+    std::vector<mp_params> par(C, mp_params{ 0.5, 0.5, 1.0 / 400.0, 0.0, 1.0, 1.0, 0.0, 0.0 });
+    if ((e = cudaMemcpy(h->d_par, par.data(), C * sizeof(mp_params), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
+    if ((e = cudaMemcpy(h->d_prop, par.data(), C * sizeof(mp_params), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
+    *out = h;
+    return MP_OK;
+}
+
+// ---- landscape
+static int upload_real(mp_engine *h, void *dst, const double *src, size_t n)
+{
+    if (is64(h)) { CK(cudaMemcpy(dst, src, n * 8, cudaMemcpyHostToDevice)); return MP_OK; }
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; i++) tmp[i] = (float)src[i];
+    CK(cudaMemcpy(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+    return MP_OK;
+}
+static int set_area(mp_engine *h, const double *area)
+{
+    h->have_area = area != nullptr;
+    if (area) {
+        for (size_t i = 0; i < nN(h); i++) REQUIRE(area[i] > 0.0, MP_ERR_ARG, "patch areas must be positive");
+        CK(cudaMemcpy(h->d_area, area, nN(h) * 8, cudaMemcpyHostToDevice));
+    }
+    return MP_OK;
+}
+int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(spacing > 0.0, MP_ERR_ARG, "spacing must be positive");
+    h->geom = MP_GEOM_LINEAR; h->spacing = spacing;
+    int rc = set_area(h, area);
+    if (rc == MP_OK) h->have_landscape = true;
+    return rc;
+}
+int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, const double *area)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(x && y, MP_ERR_ARG, "null coordinates");
+    h->geom = MP_GEOM_COORDS;
+    int rc;
+    if ((rc = upload_real(h, h->d_px, x, nN(h))) != MP_OK) return rc;
+    if ((rc = upload_real(h, h->d_py, y, nN(h))) != MP_OK) return rc;
+    rc = set_area(h, area);
+    if (rc == MP_OK) h->have_landscape = true;
+    return rc;
+}
+int mp_set_landscape_dense(mp_engine *h, const double *dist, const double *area)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(dist, MP_ERR_ARG, "null distance matrix");
+    const size_t nn = nN(h) * nN(h);
+    if (!h->d_dist) CK(cudaMalloc(&h->d_dist, nn * rsz(h)));
+    h->geom = MP_GEOM_DENSE;
+    int rc;
+    if ((rc = upload_real(h, h->d_dist, dist, nn)) != MP_OK) return rc;
+    rc = set_area(h, area);
+    if (rc == MP_OK) h->have_landscape = true;
+    return rc;
+}
+int mp_set_source_units(mp_engine *h, const double *src_unit)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    std::vector<double> u(nN(h));
+    for (size_t k = 0; k < nN(h); k++) u[k] = src_unit ? src_unit[k] : (double)(k + 1);   // loss.c:365
+    CK(cudaMemcpy(h->d_src_unit, u.data(), nN(h) * 8, cudaMemcpyHostToDevice));
+    return MP_OK;
+}
+
+// ---- data
+int mp_set_observations(mp_engine *h, const int8_t *obs)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(obs, MP_ERR_ARG, "null observations");
+    for (size_t i = 0; i < zcells(h); i++) REQUIRE(obs[i] >= -1 && obs[i] <= 1, MP_ERR_ARG, "observations must be -1, 0 or 1");
+    CK(cudaMemcpyAsync(h->d_obs, obs, zcells(h), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_obs = true;
+    return MP_OK;
+}
+int mp_set_era(mp_engine *h, const uint8_t *era)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    h->have_era = era != nullptr;
+    if (era) CK(cudaMemcpy(h->d_era, era, nT(h) - 1, cudaMemcpyHostToDevice));
+    return MP_OK;
+}
+
+// ---- chain state
+int mp_set_params(mp_engine *h, const mp_params *par)
+{
+    if (!h || !par) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    for (size_t c = 0; c < nC(h); c++) REQUIRE(par[c].K > 0.0 && par[c].alpha > 0.0, MP_ERR_ARG, "need K > 0 and alpha > 0");
+    CK(cudaMemcpyAsync(h->d_par, par, nC(h) * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+int mp_get_params(mp_engine *h, mp_params *par)
+{
+    if (!h || !par) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(par, h->d_par, nC(h) * sizeof(mp_params), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+int mp_set_state(mp_engine *h, const uint8_t *z, const uint8_t *y)
+{
+    if (!h || !z || !y) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(h->d_z, z, nC(h) * zcells(h), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_y, y, nC(h) * ycells(h), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    return MP_OK;
+}
+int mp_get_state(mp_engine *h, uint8_t *z, uint8_t *y)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    if (z) CK(cudaMemcpyAsync(z, h->d_z, nC(h) * zcells(h), cudaMemcpyDeviceToHost, h->stream));
+    if (y) CK(cudaMemcpyAsync(y, h->d_y, nC(h) * ycells(h), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+int mp_set_scales(mp_engine *h, const double *lsig)
+{
+    if (!h || !lsig) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy(h->d_lsig, lsig, nC(h) * MP_NLSIG * 8, cudaMemcpyHostToDevice));
+    return MP_OK;
+}
+int mp_get_scales(mp_engine *h, double *lsig)
+{
+    if (!h || !lsig) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(lsig, h->d_lsig, nC(h) * MP_NLSIG * 8, cudaMemcpyDeviceToHost));
+    return MP_OK;
+}
+
+// ---- likelihood
+static int check_ready(mp_engine *h)
+{
+    REQUIRE(h->have_landscape, MP_ERR_STATE, "landscape not set");
+    REQUIRE(h->have_state, MP_ERR_STATE, "chain state not set (mp_set_state or mp_init_chains)");
+    return MP_OK;
+}
+int mp_get_connectivity(mp_engine *h, double *S_out)
+{
+    if (!h || !S_out) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(S_out, h->d_S[0], nC(h) * ycells(h) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+int mp_connectivity(mp_engine *h, double *S_out)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = check_ready(h);
+    if (rc != MP_OK) return rc;
+    rc = is64(h) ? refresh_S<double>(h) : refresh_S<float>(h);
+    if (rc != MP_OK) return rc;
+    if (S_out) return mp_get_connectivity(h, S_out);
+    return MP_OK;
+}
+int mp_loglik(mp_engine *h, double *ll, double *parts)
+{
+    if (!h || !ll) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = check_ready(h);
+    if (rc != MP_OK) return rc;
+    REQUIRE(h->have_obs, MP_ERR_STATE, "observations not set");
+    rc = is64(h) ? refresh_S<double>(h) : refresh_S<float>(h);
+    if (rc != MP_OK) return rc;
+    rc = is64(h) ? loglik_resident<double>(h, nullptr, h->d_parts) : loglik_resident<float>(h, nullptr, h->d_parts);
+    if (rc != MP_OK) return rc;
+    std::vector<double> p(nC(h) * MP_NPART);
+    CK(cudaMemcpyAsync(p.data(), h->d_parts, p.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t c = 0; c < nC(h); c++) ll[c] = p[c * 4 + 0] + p[c * 4 + 1] + p[c * 4 + 2] + p[c * 4 + 3];
+    if (parts) memcpy(parts, p.data(), p.size() * 8);
+    return MP_OK;
+}
+int mp_loglik_host(mp_engine *h, const mp_params *par, const uint8_t *z, const uint8_t *y, double *ll, double *parts)
+{
+    int rc;
+    if ((rc = mp_set_params(h, par)) != MP_OK) return rc;
+    if ((rc = mp_set_state(h, z, y)) != MP_OK) return rc;
+    return mp_loglik(h, ll, parts);
+}
+extern "C++" template <typename R> int flip_delta_t(mp_engine *h, int c, int t, int k)
+{
+    Timed tm(h, MP_K_SMALL);
+    const uint8_t *era = h->have_era ? h->d_era : nullptr;
+#define FD(G) k_flip_delta<R, G><<<1, 256, 0, h->stream>>>(view<R>(h), h->d_par, (const R *)h->d_aw[0], era, h->d_z, h->d_y, \
+                                                            h->d_S[0], h->cfg.n_years, c, t, k, h->d_scalar)
+    switch (h->geom) {
+    case MP_GEOM_LINEAR: FD(MP_GEOM_LINEAR); break;
+    case MP_GEOM_COORDS: FD(MP_GEOM_COORDS); break;
+    default: FD(MP_GEOM_DENSE); break;
+    }
+#undef FD
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+int mp_flip_delta(mp_engine *h, int chain, int t, int k, double *dll)
+{
+    if (!h || !dll) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = check_ready(h);
+    if (rc != MP_OK) return rc;
+    REQUIRE(chain >= 0 && chain < h->cfg.n_chains && t >= 0 && t < h->cfg.n_years - 1 && k >= 0 && k < h->cfg.n_patches,
+            MP_ERR_ARG, "mp_flip_delta: index out of range");
+    rc = is64(h) ? launch_area_weights<double>(h, 0) : launch_area_weights<float>(h, 0);
+    if (rc != MP_OK) return rc;
+    rc = is64(h) ? flip_delta_t<double>(h, chain, t, k) : flip_delta_t<float>(h, chain, t, k);
+    if (rc != MP_OK) return rc;
+    CK(cudaMemcpyAsync(dll, h->d_scalar, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+
+// ---- sampler
+int mp_set_sampler(mp_engine *h, const mp_sampler_config *sc)
+{
+    if (!h || !sc) return MP_ERR_ARG;
+    REQUIRE(sc->n_e_steps >= 0 && sc->n_c_steps >= 0, MP_ERR_ARG, "negative sub-step count");
+    h->sc = *sc; h->have_sc = true;
+    return MP_OK;
+}
+int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
+{
+    if (!h || !sc) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(h->have_landscape && h->have_obs, MP_ERR_STATE, "set the landscape and the observations first");
+    int rc = mp_set_sampler(h, sc);
+    if (rc != MP_OK) return rc;
+    const size_t N = nN(h), T = nT(h), C = nC(h);
+    std::vector<int8_t> obs(T * N);
+    CK(cudaMemcpy(obs.data(), h->d_obs, T * N, cudaMemcpyDeviceToHost));
+    std::vector<mp_params> par(C);
+    CK(cudaMemcpy(par.data(), h->d_par, C * sizeof(mp_params), cudaMemcpyDeviceToHost));
+    std::vector<double> lsig(C * MP_NLSIG);
+    std::vector<uint8_t> z(C * T * N), y(C * (T - 1) * N);
+    for (size_t c = 0; c < C; c++) {
+        const uint32_t gc = (uint32_t)(h->cfg.chain_offset + (int)c);
+        mp_params &p = par[c];
+        if (disperse) {
+            uint4 r = rng(h->cfg.seed, gc, 0, RK_INIT_PARAM, 0, 0);
+            if (sc->sample_e) p.e = sc->e_min + u01(r.x) * (sc->e_max - sc->e_min);
+            if (sc->sample_c) p.c = sc->c_min + u01(r.y) * (sc->c_max - sc->c_min);
+            if (sc->sample_alpha) p.alpha = sc->alpha_min * pow(sc->alpha_max / sc->alpha_min, u01(r.z));
+            if (sc->sample_b) p.b = sc->b_min + u01(r.w) * (sc->b_max - sc->b_min);
+            r = rng(h->cfg.seed, gc, 0, RK_INIT_PARAM, 1, 0);
+            if (sc->sample_p) p.p = sc->p_min + u01(r.x) * (sc->p_max - sc->p_min);
+        }
+        double *ls = &lsig[c * MP_NLSIG];
+        ls[0] = log(0.05); ls[1] = log(0.1 * p.c); ls[2] = log(0.05); ls[3] = log(0.05); ls[4] = log(0.05);
+        uint8_t *zc = &z[c * T * N], *yc = &y[c * (T - 1) * N];
+        for (size_t t = 0; t < T; t++)
+            for (size_t k = 0; k < N; k++) {
+                const int o = obs[t * N + k];
+                uint8_t v;
+                if (o == 1) v = 1;
+                else if (o == 0) v = 0;
+                else if (disperse) v = u01(rng(h->cfg.seed, gc, 0, RK_INIT_Z, (uint32_t)k, (uint32_t)t).x) < 0.5;
+                else v = 1;
+                zc[t * N + k] = v;
+            }
+        for (size_t t = 0; t + 1 < T; t++)
+            for (size_t k = 0; k < N; k++) yc[t * N + k] = zc[t * N + k] && zc[(t + 1) * N + k];
+    }
+    if ((rc = mp_set_params(h, par.data())) != MP_OK) return rc;
+    if ((rc = mp_set_scales(h, lsig.data())) != MP_OK) return rc;
+    if ((rc = mp_set_state(h, z.data(), y.data())) != MP_OK) return rc;
+    h->sweep = 0; h->ndraws = 0;
+    return mp_connectivity(h, nullptr);
+}
+int mp_sweep(mp_engine *h, int nsweeps)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = check_ready(h);
+    if (rc != MP_OK) return rc;
+    REQUIRE(h->have_sc && h->have_obs, MP_ERR_STATE, "sampler not configured (mp_init_chains / mp_set_sampler)");
+    for (int s = 0; s < nsweeps; s++) {
+        rc = is64(h) ? sweep_once<double>(h) : sweep_once<float>(h);
+        if (rc != MP_OK) return rc;
+        if (h->timing && h->spans.size() > 16384) { CK(cudaStreamSynchronize(h->stream)); drain_spans(h); }
+    }
+    return MP_OK;
+}
+int mp_synchronize(mp_engine *h)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+int mp_num_draws(mp_engine *h) { return h ? h->ndraws : MP_ERR_ARG; }
+int mp_sweep_index(mp_engine *h) { return h ? (int)h->sweep : MP_ERR_ARG; }
+int mp_reset_draws(mp_engine *h) { if (!h) return MP_ERR_ARG; h->ndraws = 0; return MP_OK; }
+int mp_get_draws(mp_engine *h, int first, int count, double *out)
+{
+    if (!h || !out) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(first >= 0 && count >= 0 && first + count <= h->ndraws, MP_ERR_ARG, "mp_get_draws: range outside recorded draws");
+    const size_t row = nC(h) * MP_NDRAW * 8;
+    CK(cudaMemcpyAsync(out, (const char *)h->d_draws + (size_t)first * row, (size_t)count * row, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+
+// ---- forward simulator
+extern "C++" template <typename R> int simulate_t(mp_engine *h, const mp_params &p, const uint8_t *d_z0, int nyears, int nsims,
+                                            uint64_t seed, int era_all, uint8_t *d_zout, int32_t *d_occ, uint8_t *d_work)
+{
+    Timed tm(h, MP_K_SIM);
+    const double *area = h->have_area ? h->d_area : nullptr;
+    const int nthr = (int)std::min<size_t>(256, ((nN(h) + 31) / 32) * 32);
+#define SIM(G) k_simulate<R, G><<<nsims, nthr, 0, h->stream>>>(view<R>(h), p, area, d_z0, nyears, seed, 0u, era_all, d_zout, d_occ, d_work)
+    switch (h->geom) {
+    case MP_GEOM_LINEAR: SIM(MP_GEOM_LINEAR); break;
+    case MP_GEOM_COORDS: SIM(MP_GEOM_COORDS); break;
+    default: SIM(MP_GEOM_DENSE); break;
+    }
+#undef SIM
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+int mp_simulate(mp_engine *h, const mp_params *par, const uint8_t *z0, int nyears, int nsims, uint64_t seed, int era_all,
+                uint8_t *z_out, int32_t *occupied_out)
+{
+    if (!h || !par || !z0) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(h->have_landscape, MP_ERR_STATE, "landscape not set");
+    REQUIRE(nyears >= 1 && nsims >= 1 && par->K > 0.0, MP_ERR_ARG, "mp_simulate: need nyears>=1, nsims>=1, K>0");
+    const size_t N = nN(h);
+    uint8_t *d_z0 = nullptr, *d_zout = nullptr, *d_work = nullptr;
+    int32_t *d_occ = nullptr;
+    int rc = MP_OK;
+    cudaError_t e;
+#define SIMCK(call) if ((e = (call)) != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e); rc = MP_ERR_CUDA; goto done; }
+    SIMCK(cudaMalloc(&d_z0, N));
+    SIMCK(cudaMalloc(&d_work, (size_t)nsims * 2 * N));
+    if (z_out) SIMCK(cudaMalloc(&d_zout, (size_t)nsims * (nyears + 1) * N));
+    if (occupied_out) SIMCK(cudaMalloc(&d_occ, (size_t)nsims * (nyears + 1) * 4));
+    SIMCK(cudaMemcpyAsync(d_z0, z0, N, cudaMemcpyHostToDevice, h->stream));
+    rc = is64(h) ? simulate_t<double>(h, *par, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work)
+                 : simulate_t<float>(h, *par, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work);
+    if (rc != MP_OK) goto done;
+    if (z_out) SIMCK(cudaMemcpyAsync(z_out, d_zout, (size_t)nsims * (nyears + 1) * N, cudaMemcpyDeviceToHost, h->stream));
+    if (occupied_out) SIMCK(cudaMemcpyAsync(occupied_out, d_occ, (size_t)nsims * (nyears + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+    SIMCK(cudaStreamSynchronize(h->stream));
+#undef SIMCK
+done:
+    cudaFree(d_z0); cudaFree(d_work); cudaFree(d_zout); cudaFree(d_occ);
+    return rc;
+}
+
+// ---- plumbing
+int mp_device_ptr(mp_engine *h, int which, void **ptr, size_t *bytes)
+{
+    if (!h || !ptr) return MP_ERR_ARG;
+    size_t b = 0; void *p = nullptr;
+    switch (which) {
+    case MP_BUF_DRAWS: p = h->d_draws; b = std::max<size_t>(1, (size_t)h->cfg.max_draws) * nC(h) * MP_NDRAW * 8; break;
+    case MP_BUF_Z: p = h->d_z; b = nC(h) * zcells(h); break;
+    case MP_BUF_Y: p = h->d_y; b = nC(h) * ycells(h); break;
+    case MP_BUF_S: p = h->d_S[0]; b = nC(h) * ycells(h) * 8; break;
+    case MP_BUF_PARAMS: p = h->d_par; b = nC(h) * sizeof(mp_params); break;
+    default: h->err = "mp_device_ptr: unknown buffer"; return MP_ERR_ARG;
+    }
+    *ptr = p;
+    if (bytes) *bytes = b;
+    return MP_OK;
+}
+int mp_get_stream(mp_engine *h, void **stream)
+{
+    if (!h || !stream) return MP_ERR_ARG;
+    *stream = (void *)h->stream;
+    return MP_OK;
+}
+int mp_set_timing(mp_engine *h, int enabled)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    drain_spans(h);
+    h->timing = enabled != 0;
+    return MP_OK;
+}
+int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    drain_spans(h);
+    for (int i = 0; i < MP_K_NCAT; i++) {
+        if (ms) ms[i] = h->t_ms[i];
+        if (launches) launches[i] = h->t_launch[i];
+        if (reset) { h->t_ms[i] = 0.0; h->t_launch[i] = 0; }
+    }
+    return MP_OK;
+}
+int mp_probe_peaks(mp_engine *h, double *out4)
+{
+    if (!h || !out4) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    const int nsm = prop.multiProcessorCount, blocks = nsm * 4, thr = 512, iters = 4096;
+    float *d_f = nullptr; double *d_d = nullptr;
+    CK(cudaMalloc(&d_f, 64)); CK(cudaMalloc(&d_d, 64));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    auto timeit = [&](auto launch) -> double {
+        launch(); cudaStreamSynchronize(h->stream);
+        double best = 1e30;
+        for (int r = 0; r < 5; r++) {
+            cudaEventRecord(a, h->stream); launch(); cudaEventRecord(b, h->stream); cudaEventSynchronize(b);
+            float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+            best = std::min(best, (double)ms);
+        }
+        return best * 1e-3;
+    };
+    const double work = (double)blocks * thr * iters;
+    double s = timeit([&] { k_probe_mufu<<<blocks, thr, 0, h->stream>>>(d_f, iters); });
+    out4[0] = work * 4 / s * 1e-9;
+    s = timeit([&] { k_probe_ffma<<<blocks, thr, 0, h->stream>>>(d_f, iters); });
+    out4[1] = work * 8 / s * 1e-9;
+    s = timeit([&] { k_probe_dadd<<<blocks, thr, 0, h->stream>>>(d_d, iters); });
+    out4[2] = work * 8 / s * 1e-9;
+    const size_t bytes = (size_t)1 << 30;
+    float4 *src = nullptr, *dst = nullptr;
+    CK(cudaMalloc(&src, bytes)); CK(cudaMalloc(&dst, bytes));
+    CK(cudaMemsetAsync(src, 1, bytes, h->stream));
+    s = timeit([&] { k_probe_copy<<<nsm * 16, 512, 0, h->stream>>>(src, dst, bytes / 16); });
+    out4[3] = 2.0 * (double)bytes / s * 1e-9;
+    cudaFree(src); cudaFree(dst); cudaFree(d_f); cudaFree(d_d);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,621 @@
+// mp_kernels.cuh -- the CUDA kernels of the SPOM engine (sm_100a).  Included by mp_engine.cu only.
+//
+//  k_pack_y        y bytes -> one 32-year bit word per (chain, patch)      (feeds k_conn)
+//  k_area_weights  aw[set][chain][l] = A_l^b
+//  k_conn          fused on-the-fly dispersal-kernel x occupancy contraction  (main_MIDASPOM.c:350-358)
+//  k_col_ll        colonisation log-terms + per-chain segmented reduction      (compPePc:40,44)
+//  k_counts        integer bookkeeping: extinction / detection / prior counts  (compPePc:38-39)
+//  k_flip_delta    rank-1 log-odds of one intermediate-state flip
+//  k_sweep_y       Gibbs scan of y_t | z with rank-1 updates of S_t in shared memory
+//  k_update_z      Gibbs update of latent occupancy cells (conditionally independent given y)
+//  k_propose_* / k_decide_* / k_update_ep / k_record   Metropolis bookkeeping, one warp per chain
+//  k_simulate      forward simulator (future.c:64-110)
+#pragma once
+#include "mp_device.cuh"
+
+namespace mp {
+
+constexpr int CONN_TILE = 128;      // targets per CTA == sources per shared-memory tile
+constexpr int COL_THREADS = 256;
+constexpr int MAX_COL_BLOCKS = 64;  // partial sums per chain (fixed => deterministic reduction order)
+constexpr int NCOUNT = 12;          // per-chain integer counters, see k_counts
+enum { CNT_N10 = 0, CNT_N10P = 1, CNT_N11 = 2, CNT_N11P = 3, CNT_BADEXT = 4, CNT_ND = 5, CNT_NM = 6,
+       CNT_BADDET = 7, CNT_LAT1 = 8, CNT_LAT0 = 9, CNT_SY = 10, CNT_SZ = 11 };
+
+// ------------------------------------------------------------------ packing
+__global__ void k_pack_y(const uint8_t *__restrict__ y, uint32_t *__restrict__ ybits, int n, int ntrans, int nwords)
+{
+    const int c = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const uint8_t *yc = y + (size_t)c * ntrans * n;
+    for (int w = 0; w < nwords; w++) {
+        uint32_t bits = 0;
+        const int t1 = min(32, ntrans - 32 * w);
+        for (int t = 0; t < t1; t++) bits |= (uint32_t)(yc[(size_t)(32 * w + t) * n + l] != 0) << t;
+        ybits[((size_t)c * nwords + w) * n + l] = bits;
+    }
+}
+
+template <typename R>
+__global__ void k_area_weights(const mp_params *__restrict__ par, const double *__restrict__ area, R *__restrict__ aw, int n)
+{
+    const int c = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const double b = par[c].b;
+    aw[(size_t)c * n + l] = (area && b != 0.0) ? (R)pow(area[l], b) : (R)1;
+}
+
+// ------------------------------------------------------------------ connectivity
+// One thread per target patch k, one CTA per (128 targets, chain, parameter set).  Sources are
+// staged 128 at a time in shared memory (coordinates, area weight, year bit word); the dispersal
+// weight is evaluated once per (target, source) pair and added to every year in which the source
+// is occupied.  Accumulation is FP64 in both precisions so that the later rank-1 downdates of
+// k_sweep_y cancel exactly.
+template <typename R> struct ConnArgs {
+    Landscape<R> ls;
+    const mp_params *par[2];
+    const R *aw[2];
+    double *S[2];
+    const uint32_t *ybits;
+    int ntrans, nwords;
+};
+
+template <typename R, int GEOM, int NYB>
+__global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
+{
+    __shared__ R sx[CONN_TILE], sy[CONN_TILE], saw[CONN_TILE];
+    __shared__ uint32_t sbits[CONN_TILE];
+    const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
+    const int k = blockIdx.x * CONN_TILE + tid;
+    const R alpha = (R)a.par[set][c].alpha;
+    const R *aw = a.aw[set] + (size_t)c * n;
+    R tx = 0, ty = 0;
+    if (GEOM == MP_GEOM_COORDS && k < n) { tx = a.ls.px[k]; ty = a.ls.py[k]; }
+    for (int w = 0; w < a.nwords; w++) {
+        const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
+        double acc[NYB];
+#pragma unroll
+        for (int t = 0; t < NYB; t++) acc[t] = 0.0;
+        for (int l0 = 0; l0 < n; l0 += CONN_TILE) {
+            const int l = l0 + tid;
+            if (l < n) {
+                if (GEOM == MP_GEOM_COORDS) { sx[tid] = a.ls.px[l]; sy[tid] = a.ls.py[l]; }
+                saw[tid] = aw[l]; sbits[tid] = bw[l];
+            } else sbits[tid] = 0;
+            __syncthreads();
+            if (k < n) {
+#pragma unroll 4
+                for (int j = 0; j < CONN_TILE; j++) {
+                    const uint32_t bits = sbits[j];
+                    if (bits == 0 || l0 + j == k) continue;       // l != k  (main_MIDASPOM.c:354)
+                    const R wgt = saw[j] * kernel_factor<R, GEOM>(a.ls, alpha, k, l0 + j, tx, ty, sx[j], sy[j]);
+                    const double wd = (double)wgt;
+#pragma unroll
+                    for (int t = 0; t < NYB; t++) if (bits & (1u << t)) acc[t] += wd;
+                }
+            }
+            __syncthreads();
+        }
+        if (k < n) {
+            double *S = a.S[set] + (size_t)c * a.ntrans * n;
+#pragma unroll
+            for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) S[(size_t)(32 * w + t) * n + k] = acc[t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ colonisation log-likelihood
+// Sum over cells (t,k) with y=0 of  z'? log C : log(1-C)  (-inf for y=1,z'=0), per chain.
+// Grid (nblk, chains, nsets); fixed block->cell mapping and a fixed-order second stage make the
+// per-chain sum deterministic.
+struct ColArgs {
+    const mp_params *par[2];
+    const double *S[2];
+    double *partial[2];      // [chain][nblk]
+};
+template <typename R>
+__global__ void __launch_bounds__(COL_THREADS) k_col_ll(ColArgs a, Landscape<R> ls, const uint8_t *__restrict__ z,
+                                                        const uint8_t *__restrict__ y, const uint8_t *__restrict__ era,
+                                                        int T)
+{
+    __shared__ double scratch[32];
+    const int n = ls.n, c = blockIdx.y, set = blockIdx.z, ntrans = T - 1;
+    const mp_params p = a.par[set][c];
+    const double *S = a.S[set] + (size_t)c * ntrans * n;
+    const uint8_t *zc = z + (size_t)c * T * n, *yc = y + (size_t)c * ntrans * n;
+    double acc = 0.0;
+    const long long cells = (long long)ntrans * n;
+    const Trans<R> tr0 = make_trans<R>(p, 0), tr1 = make_trans<R>(p, 1);
+    for (long long i = (long long)blockIdx.x * COL_THREADS + threadIdx.x; i < cells; i += (long long)gridDim.x * COL_THREADS) {
+        const int t = (int)(i / n), k = (int)(i - (long long)t * n);
+        const int zn = zc[i + n];
+        if (yc[i]) { if (!zn) acc += -INFINITY; continue; }
+        const Trans<R> tr = pick_trans<R>(tr0, tr1, era ? era[t] != 0 : 0);
+        const R C = col_prob<R>(tr, (R)S[i], source_term<R>(ls, tr, k));
+        acc += (double)log_col<R>(zn, C);
+    }
+    const double tot = block_sum(acc, scratch);
+    if (threadIdx.x == 0) a.partial[set][(size_t)c * gridDim.x + blockIdx.x] = tot;
+}
+// fixed-order sum of the per-block partials of one chain by one warp
+__device__ __forceinline__ double reduce_partials(const double *partial, int nblk)
+{
+    const int lane = threadIdx.x & 31;
+    double v = 0.0;
+    for (int i = lane; i < nblk; i += 32) v += partial[i];
+    return warp_sum(v);
+}
+
+// ------------------------------------------------------------------ integer bookkeeping
+// Per chain: extinction counts by era (#(z=1,y=0), #(z=1,y=1); compPePc:38-39), impossible cells,
+// detection counts, latent year-0 cells by state, totals.  Integer atomics => order independent.
+__global__ void k_counts(const int8_t *__restrict__ obs, const uint8_t *__restrict__ era, const uint8_t *__restrict__ z,
+                         const uint8_t *__restrict__ y, unsigned long long *__restrict__ counts, int n, int T, int detect)
+{
+    __shared__ unsigned int sc[NCOUNT];
+    const int c = blockIdx.y, ntrans = T - 1;
+    if (threadIdx.x < NCOUNT) sc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int loc[NCOUNT];
+#pragma unroll
+    for (int i = 0; i < NCOUNT; i++) loc[i] = 0;
+    const uint8_t *zc = z + (size_t)c * T * n, *yc = y + (size_t)c * ntrans * n;
+    const long long cells = (long long)T * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / n);
+        const int zz = zc[i] != 0, o = obs[i];
+        loc[CNT_SZ] += zz;
+        if (t < ntrans) {
+            const int yy = yc[i] != 0, pre = era ? era[t] != 0 : 0;
+            loc[CNT_SY] += yy;
+            if (zz) { if (yy) loc[CNT_N11 + pre]++; else loc[CNT_N10 + pre]++; }
+            else if (yy) loc[CNT_BADEXT]++;
+        }
+        if (o == 1) { if (zz) loc[CNT_ND]++; else loc[CNT_BADDET]++; }
+        else if (o == 0 && zz) { if (detect) loc[CNT_NM]++; else loc[CNT_BADDET]++; }
+        if (t == 0 && (o == -1 || (detect && o == 0))) { if (zz) loc[CNT_LAT1]++; else loc[CNT_LAT0]++; }
+    }
+#pragma unroll
+    for (int i = 0; i < NCOUNT; i++) if (loc[i]) atomicAdd(&sc[i], loc[i]);
+    __syncthreads();
+    if (threadIdx.x < NCOUNT && sc[threadIdx.x]) atomicAdd(&counts[(size_t)c * NCOUNT + threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+}
+
+__device__ __forceinline__ double xlogd(unsigned long long cnt, double v) { return cnt ? (double)cnt * log(v) : 0.0; }
+__device__ inline double ll_ext_counts(const mp_params &p, const unsigned long long *cn)
+{
+    if (cn[CNT_BADEXT]) return -INFINITY;
+    double E0 = p.e > 1.0 ? 1.0 : p.e, E1 = p.e / p.K > 1.0 ? 1.0 : p.e / p.K;
+    return xlogd(cn[CNT_N10], E0) + xlogd(cn[CNT_N11], 1.0 - E0) + xlogd(cn[CNT_N10P], E1) + xlogd(cn[CNT_N11P], 1.0 - E1);
+}
+__device__ inline double ll_det_counts(const mp_params &p, const unsigned long long *cn, int detect)
+{
+    if (cn[CNT_BADDET]) return -INFINITY;
+    if (!detect) return 0.0;
+    return xlogd(cn[CNT_ND], p.p) + xlogd(cn[CNT_NM], 1.0 - p.p);
+}
+__device__ inline double ll_prior_counts(double p0, const unsigned long long *cn)
+{
+    return xlogd(cn[CNT_LAT1], p0) + xlogd(cn[CNT_LAT0], 1.0 - p0);
+}
+
+// ------------------------------------------------------------------ Metropolis bookkeeping (one warp per chain)
+struct SamplerDev {
+    mp_sampler_config sc;
+    uint64_t seed;
+    int chain_offset;
+    int detect;
+    double p0;
+};
+__device__ __forceinline__ double adapt_gain(uint32_t sweep) { return 1.0 / pow((double)sweep + 1.0, 0.6); }
+
+// flags[c*4+0] = proposal in bounds, +1 = accepted, +2/+3 spare ; logu[c] = log of the MH uniform
+__global__ void k_propose_ab(SamplerDev sd, uint32_t sweep, const mp_params *__restrict__ par, mp_params *__restrict__ prop,
+                             const double *__restrict__ lsig, int *__restrict__ flags, double *__restrict__ logu, int nchains)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchains) return;
+    const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_AB, 0, 0);
+    double n1, n2;
+    box_muller(r.x, r.y, n1, n2);
+    mp_params q = par[c];
+    if (sd.sc.sample_alpha) q.alpha = q.alpha * exp(exp(lsig[c * MP_NLSIG + 2]) * n1);
+    if (sd.sc.sample_b) q.b = q.b + exp(lsig[c * MP_NLSIG + 3]) * n2;
+    prop[c] = q;
+    flags[c * 4 + 0] = q.alpha >= sd.sc.alpha_min && q.alpha <= sd.sc.alpha_max && q.b >= sd.sc.b_min && q.b <= sd.sc.b_max;
+    flags[c * 4 + 1] = 0;
+    logu[c] = log(u01(r.z));
+}
+// llc[c] receives the colonisation log-likelihood of the state kept
+__global__ void k_decide_ab(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
+                            double *__restrict__ lsig, int *__restrict__ flags, const double *__restrict__ logu,
+                            const double *__restrict__ part_cur, const double *__restrict__ part_prop, int nblk,
+                            double *__restrict__ llc, int do_mh)
+{
+    const int c = blockIdx.x;
+    const double cur = reduce_partials(part_cur + (size_t)c * nblk, nblk);
+    double pr = 0.0;
+    if (do_mh) pr = reduce_partials(part_prop + (size_t)c * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    int acc = 0;
+    double keep = cur;
+    if (do_mh) {
+        const double d = pr - cur;
+        if (flags[c * 4 + 0] && !isnan(d) && logu[c] < d) { acc = 1; keep = pr; par[c] = prop[c]; }
+        flags[c * 4 + 1] = acc;
+        if (sweep < (uint32_t)sd.sc.n_adapt) {
+            const double g = adapt_gain(sweep);
+            if (sd.sc.sample_alpha) lsig[c * MP_NLSIG + 2] += g * (acc - 0.30);
+            if (sd.sc.sample_b) lsig[c * MP_NLSIG + 3] += g * (acc - 0.30);
+        }
+    }
+    llc[c] = keep;
+}
+// S_cur <- S_prop, aw_cur <- aw_prop for accepted chains
+template <typename R>
+__global__ void k_commit_ab(const int *__restrict__ flags, double *__restrict__ S_cur, const double *__restrict__ S_prop,
+                            R *__restrict__ aw_cur, const R *__restrict__ aw_prop, long long cells, int n)
+{
+    const int c = blockIdx.y;
+    if (!flags[c * 4 + 1]) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        S_cur[(size_t)c * cells + i] = S_prop[(size_t)c * cells + i];
+        if (i < n) aw_cur[(size_t)c * n + i] = aw_prop[(size_t)c * n + i];
+    }
+}
+__global__ void k_propose_c(SamplerDev sd, uint32_t sweep, int step, const mp_params *__restrict__ par,
+                            mp_params *__restrict__ prop, const double *__restrict__ lsig, int *__restrict__ flags,
+                            double *__restrict__ logu, int nchains)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchains) return;
+    const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_C, (uint32_t)step, 0);
+    double n1, n2;
+    box_muller(r.x, r.y, n1, n2);
+    mp_params q = par[c];
+    q.c = q.c + exp(lsig[c * MP_NLSIG + 1]) * n1;
+    prop[c] = q;
+    flags[c * 4 + 0] = q.c >= sd.sc.c_min && q.c <= sd.sc.c_max;
+    logu[c] = log(u01(r.z));
+}
+__global__ void k_decide_c(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
+                           double *__restrict__ lsig, const int *__restrict__ flags, const double *__restrict__ logu,
+                           const double *__restrict__ part_prop, int nblk, double *__restrict__ llc)
+{
+    const int c = blockIdx.x;
+    const double pr = reduce_partials(part_prop + (size_t)c * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    const double d = pr - llc[c];
+    int acc = 0;
+    if (flags[c * 4 + 0] && !isnan(d) && logu[c] < d) { acc = 1; par[c] = prop[c]; llc[c] = pr; }
+    if (sweep < (uint32_t)sd.sc.n_adapt) lsig[c * MP_NLSIG + 1] += adapt_gain(sweep) * (acc - 0.44);
+}
+// e and p from the sufficient counts: random-walk MH sub-steps, one thread per chain
+__global__ void k_update_ep(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, double *__restrict__ lsig,
+                            const unsigned long long *__restrict__ counts, int nchains)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchains) return;
+    const unsigned long long *cn = counts + (size_t)c * NCOUNT;
+    mp_params p = par[c];
+    const bool adapting = sweep < (uint32_t)sd.sc.n_adapt;
+    const double g = adapt_gain(sweep);
+    if (sd.sc.sample_e) {
+        double ll = ll_ext_counts(p, cn), ls = lsig[c * MP_NLSIG + 0];
+        for (int s = 0; s < sd.sc.n_e_steps; s++) {
+            const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_E, (uint32_t)s, 0);
+            double n1, n2;
+            box_muller(r.x, r.y, n1, n2);
+            mp_params q = p;
+            q.e = p.e + exp(ls) * n1;
+            int acc = 0;
+            if (q.e >= sd.sc.e_min && q.e <= sd.sc.e_max) {
+                const double l2 = ll_ext_counts(q, cn), d = l2 - ll;
+                if (!isnan(d) && log(u01(r.z)) < d) { acc = 1; p = q; ll = l2; }
+            }
+            if (adapting) ls += g * (acc - 0.44);
+        }
+        lsig[c * MP_NLSIG + 0] = ls;
+    }
+    if (sd.sc.sample_p && sd.detect) {
+        double ll = ll_det_counts(p, cn, 1), ls = lsig[c * MP_NLSIG + 4];
+        for (int s = 0; s < sd.sc.n_e_steps; s++) {
+            const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_P, (uint32_t)s, 0);
+            double n1, n2;
+            box_muller(r.x, r.y, n1, n2);
+            mp_params q = p;
+            q.p = p.p + exp(ls) * n1;
+            int acc = 0;
+            if (q.p >= sd.sc.p_min && q.p <= sd.sc.p_max) {
+                const double l2 = ll_det_counts(q, cn, 1), d = l2 - ll;
+                if (!isnan(d) && log(u01(r.z)) < d) { acc = 1; p = q; ll = l2; }
+            }
+            if (adapting) ls += g * (acc - 0.44);
+        }
+        lsig[c * MP_NLSIG + 4] = ls;
+    }
+    par[c] = p;
+}
+// draws[c] = (e, c, alpha, b, p, loglik, #y=1, #z=1); parts (nullable) = ext, col, prior, det
+__global__ void k_record(SamplerDev sd, const mp_params *__restrict__ par, const unsigned long long *__restrict__ counts,
+                         const double *__restrict__ part_cur, int nblk, double *__restrict__ draw, double *__restrict__ parts)
+{
+    const int c = blockIdx.x;
+    const double lc = reduce_partials(part_cur + (size_t)c * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    const unsigned long long *cn = counts + (size_t)c * NCOUNT;
+    const mp_params p = par[c];
+    const double le = ll_ext_counts(p, cn), lp = ll_prior_counts(sd.p0, cn), ld = ll_det_counts(p, cn, sd.detect);
+    if (draw) {
+        double *d = draw + (size_t)c * MP_NDRAW;
+        d[0] = p.e; d[1] = p.c; d[2] = p.alpha; d[3] = p.b; d[4] = p.p; d[5] = le + lc + lp + ld;
+        d[6] = (double)cn[CNT_SY]; d[7] = (double)cn[CNT_SZ];
+    }
+    if (parts) { double *q = parts + (size_t)c * MP_NPART; q[0] = le; q[1] = lc; q[2] = lp; q[3] = ld; }
+}
+
+// ------------------------------------------------------------------ latent occupancy cells
+// z_tk | y, theta for every latent cell at once: S depends on y only, so the cells are
+// conditionally independent.  Forced to 1 when an adjacent intermediate state is 1.
+template <typename R>
+__global__ void k_update_z(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par,
+                           const int8_t *__restrict__ obs, const uint8_t *__restrict__ era, uint8_t *__restrict__ z,
+                           const uint8_t *__restrict__ y, const double *__restrict__ S, int T)
+{
+    const int n = ls.n, c = blockIdx.y, ntrans = T - 1;
+    const long long cells = (long long)T * n;
+    const mp_params p = par[c];
+    uint8_t *zc = z + (size_t)c * cells;
+    const uint8_t *yc = y + (size_t)c * ntrans * n;
+    const double *Sc = S + (size_t)c * ntrans * n;
+    const Trans<R> tr0 = make_trans<R>(p, 0), tr1 = make_trans<R>(p, 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const int o = obs[i];
+        if (!(o == -1 || (sd.detect && o == 0))) continue;
+        const int t = (int)(i / n), k = (int)(i - (long long)t * n);
+        const bool forced = (t > 0 && yc[i - n]) || (t < ntrans && yc[i]);
+        if (forced) { zc[i] = 1; continue; }
+        R lo = 0;
+        if (t > 0) {
+            const Trans<R> tr = pick_trans<R>(tr0, tr1, era ? era[t - 1] != 0 : 0);
+            const R C = col_prob<R>(tr, (R)Sc[i - n], source_term<R>(ls, tr, k));
+            lo += Num<R>::logv(C) - Num<R>::log1m(C);
+        }
+        if (t < ntrans) lo += (era && era[t]) ? tr1.logE : tr0.logE;
+        double lod = (double)lo;
+        if (t == 0) lod += log(sd.p0) - log(1.0 - sd.p0);
+        if (sd.detect && o == 0) lod += log(1.0 - p.p);
+        const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_Z, (uint32_t)k, (uint32_t)t);
+        zc[i] = isnan(lod) ? 0 : (logit_u(r.x) < lod);
+    }
+}
+
+// ------------------------------------------------------------------ rank-1 flip of the intermediate state
+// Contribution of target q to the log-odds of flipping source k (current value cur), and the
+// updated (S, L) of q.  Shared by k_flip_delta and k_sweep_y so both use identical arithmetic.
+template <typename R, int GEOM>
+__device__ __forceinline__ R flip_pair(const Landscape<R> &ls, const Trans<R> &tr, R awk, int k, R kx, R ky, int q,
+                                       int cur, bool zero_after, double Sq, int yq, int znq, R Lq, bool haveL,
+                                       double &S_alt, R &L_alt)
+{
+    R qx = 0, qy = 0;
+    if (GEOM == MP_GEOM_COORDS) { qx = ls.px[q]; qy = ls.py[q]; }
+    const R w = awk * kernel_factor<R, GEOM>(ls, tr.alpha, q, k, qx, qy, kx, ky);
+    double sa = cur ? Sq - (double)w : Sq + (double)w;
+    if (zero_after || sa < 0.0) sa = 0.0;
+    S_alt = sa;
+    if (yq) { L_alt = 0; return 0; }
+    const R g = source_term<R>(ls, tr, q);
+    const R la = log_col<R>(znq, col_prob<R>(tr, (R)sa, g));
+    const R lc = haveL ? Lq : log_col<R>(znq, col_prob<R>(tr, (R)Sq, g));
+    L_alt = la;
+    return ldiff<R>(la, lc);
+}
+// own-cell term of candidate k (z_t = z_t+1 = 1): y=1 -> log(1-E) ; y=0 -> log E + log C_k
+template <typename R>
+__device__ __forceinline__ R flip_own(const Landscape<R> &ls, const Trans<R> &tr, int k, int cur, double Sk)
+{
+    const R l1 = tr.log1mE;
+    const R l0 = tr.logE + Num<R>::logv(col_prob<R>(tr, (R)Sk, source_term<R>(ls, tr, k)));
+    return cur ? ldiff<R>(l0, l1) : ldiff<R>(l1, l0);
+}
+
+template <typename R, int GEOM>
+__global__ void k_flip_delta(Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
+                             const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, const uint8_t *__restrict__ y,
+                             const double *__restrict__ S, int T, int c, int t, int k, double *__restrict__ out)
+{
+    __shared__ double scratch[32];
+    const int n = ls.n, ntrans = T - 1;
+    const Trans<R> tr = make_trans<R>(par[c], era ? era[t] : 0);
+    const uint8_t *yt = y + ((size_t)c * ntrans + t) * n, *zn = z + ((size_t)c * T + t + 1) * n;
+    const double *St = S + ((size_t)c * ntrans + t) * n;
+    const int cur = yt[k];
+    int nocc = 0;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) nocc += yt[q];
+    nocc = (int)(block_sum((double)nocc, scratch) + 0.5);
+    __syncthreads();
+    const bool zero_after = (nocc + (cur ? -1 : 1)) == 0;
+    R kx = 0, ky = 0;
+    if (GEOM == MP_GEOM_COORDS) { kx = ls.px[k]; ky = ls.py[k]; }
+    const R awk = aw[(size_t)c * n + k];
+    double acc = 0.0;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        if (q == k) { acc += (double)flip_own<R>(ls, tr, k, cur, St[k]); continue; }
+        double sa; R la;
+        acc += (double)flip_pair<R, GEOM>(ls, tr, awk, k, kx, ky, q, cur, zero_after, St[q], yt[q], zn[q], (R)0, false, sa, la);
+    }
+    const double tot = block_sum(acc, scratch);
+    if (threadIdx.x == 0) *out = isnan(tot) ? -INFINITY : tot;
+}
+
+// One CTA per (chain, transition): S_t (FP64), the cached log-terms L (R) and the cell flags live
+// in shared memory for the whole scan.  Candidates (z_t = z_t+1 = 1) are visited in patch order;
+// each visit evaluates the N-wide rank-1 change, reduces it in a fixed order, and every thread
+// takes the same decision from logit(u) < delta with u = Philox(seed, chain, sweep, RK_Y, k, t).
+template <typename R, int GEOM, int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
+          const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S, int T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, nthr = blockDim.x;
+    const int c = blockIdx.x / ntrans, t = blockIdx.x - c * ntrans;
+    double *sS = reinterpret_cast<double *>(smem_raw);
+    R *sL = reinterpret_cast<R *>(sS + n);
+    uint8_t *sF = reinterpret_cast<uint8_t *>(sL + n);        // bit0 y, bit1 z_t, bit2 z_t+1
+    __shared__ double warp_part[2][32];
+    __shared__ double thr_slot[2];
+    __shared__ double scratch[32];
+
+    const Trans<R> tr = make_trans<R>(par[c], era ? era[t] : 0);
+    uint8_t *yt = y + ((size_t)c * ntrans + t) * n;
+    const uint8_t *zt = z + ((size_t)c * T + t) * n, *zn = zt + n;
+    double *St = S + ((size_t)c * ntrans + t) * n;
+    const R *awc = aw + (size_t)c * n;
+
+    int nocc_loc = 0;
+    for (int q = tid; q < n; q += nthr) {
+        const int yq = yt[q] != 0, znq = zn[q] != 0;
+        const double s = St[q];
+        sS[q] = s;
+        sF[q] = (uint8_t)(yq | ((zt[q] != 0) << 1) | (znq << 2));
+        sL[q] = yq ? (R)0 : log_col<R>(znq, col_prob<R>(tr, (R)s, source_term<R>(ls, tr, q)));
+        nocc_loc += yq;
+    }
+    int nocc = (int)(block_sum((double)nocc_loc, scratch) + 0.5);
+    __syncthreads();
+
+    const uint32_t gchain = (uint32_t)(sd.chain_offset + c);
+    int it = 0;
+    for (int k = 0; k < n; k++) {
+        const int fk = sF[k];
+        if ((fk & 6) != 6) continue;                    // candidate iff z_t[k] = z_t+1[k] = 1
+        const int par_i = it & 1; it++;
+        const int cur = fk & 1;
+        const bool zero_after = (nocc + (cur ? -1 : 1)) == 0;
+        if (tid == 0) thr_slot[par_i] = logit_u(rng(sd.seed, gchain, sweep, RK_Y, (uint32_t)k, (uint32_t)t).x);
+        R kx = 0, ky = 0;
+        if (GEOM == MP_GEOM_COORDS) { kx = ls.px[k]; ky = ls.py[k]; }
+        const R awk = awc[k];
+        double acc = 0.0;
+        for (int q = tid; q < n; q += nthr) {
+            if (q == k) { acc += (double)flip_own<R>(ls, tr, k, cur, sS[k]); continue; }
+            double sa; R la;
+            const int fq = sF[q];
+            acc += (double)flip_pair<R, GEOM>(ls, tr, awk, k, kx, ky, q, cur, zero_after, sS[q], fq & 1, (fq >> 2) & 1,
+                                              sL[q], true, sa, la);
+        }
+        // fixed-order block reduction; every warp redoes the final tree so all threads agree
+        const int lane = tid & 31, wid = tid >> 5, nw = (nthr + 31) >> 5;
+        acc = warp_sum(acc);
+        if (lane == 0) warp_part[par_i][wid] = acc;
+        __syncthreads();
+        double tot = warp_sum(lane < nw ? warp_part[par_i][lane] : 0.0);
+        if (isnan(tot)) tot = -INFINITY;
+        const bool flip = thr_slot[par_i] < tot;
+        if (flip) {
+            // recompute and commit: each thread rewrites the (S, L) of its own targets
+            for (int q = tid; q < n; q += nthr) {
+                if (q == k) { sF[k] = (uint8_t)(fk ^ 1);
+                              sL[k] = cur ? log_col<R>(1, col_prob<R>(tr, (R)sS[k], source_term<R>(ls, tr, k))) : (R)0;
+                              continue; }
+                double sa; R la;
+                const int fq = sF[q];
+                flip_pair<R, GEOM>(ls, tr, awk, k, kx, ky, q, cur, zero_after, sS[q], fq & 1, (fq >> 2) & 1, sL[q], true, sa, la);
+                sS[q] = sa;
+                if (!(fq & 1)) sL[q] = la;
+            }
+            nocc += cur ? -1 : 1;
+        }
+    }
+    __syncthreads();
+    for (int q = tid; q < n; q += nthr) { St[q] = sS[q]; yt[q] = sF[q] & 1; }
+}
+
+// ------------------------------------------------------------------ forward simulator
+// One CTA per simulated trajectory (future.c:359-386 loops over simulations; simpij :64-110 is one
+// year).  survive iff u > E (:78); colonise iff u < C (:100).
+template <typename R, int GEOM>
+__global__ void k_simulate(Landscape<R> ls, mp_params p, const double *__restrict__ area, const uint8_t *__restrict__ z0,
+                           int nyears, uint64_t seed, uint32_t sim0, int era_all, uint8_t *__restrict__ z_out,
+                           int32_t *__restrict__ occ_out, uint8_t *__restrict__ work)
+{
+    __shared__ double scratch[32];
+    const int n = ls.n, tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t sim = sim0 + blockIdx.x;
+    uint8_t *zc = work + (size_t)blockIdx.x * 2 * n, *yc = zc + n;     // current state, intermediate state
+    const Trans<R> tr = make_trans<R>(p, era_all);
+    int cnt = 0;
+    for (int k = tid; k < n; k += nthr) { zc[k] = z0[k] != 0; cnt += zc[k];
+                                           if (z_out) z_out[(size_t)blockIdx.x * (nyears + 1) * n + k] = zc[k]; }
+    cnt = (int)(block_sum((double)cnt, scratch) + 0.5);
+    if (tid == 0 && occ_out) occ_out[(size_t)blockIdx.x * (nyears + 1)] = cnt;
+    __syncthreads();
+    for (int t = 0; t < nyears; t++) {
+        for (int k = tid; k < n; k += nthr) {
+            const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_EXT, (uint32_t)k, 0);
+            yc[k] = zc[k] && (u01(r.x) > (double)tr.E);
+        }
+        __syncthreads();
+        int c2 = 0;
+        for (int k = tid; k < n; k += nthr) {
+            R kx = 0, ky = 0;
+            if (GEOM == MP_GEOM_COORDS) { kx = ls.px[k]; ky = ls.py[k]; }
+            double s = 0.0;
+            for (int l = 0; l < n; l++) {
+                if (l == k || !yc[l]) continue;
+                R lx = 0, ly = 0;
+                if (GEOM == MP_GEOM_COORDS) { lx = ls.px[l]; ly = ls.py[l]; }
+                R w = kernel_factor<R, GEOM>(ls, tr.alpha, k, l, kx, ky, lx, ly);
+                if (area && p.b != 0.0) w *= (R)pow(area[l], p.b);
+                s += (double)w;
+            }
+            const R C = col_prob<R>(tr, (R)s, source_term<R>(ls, tr, k));
+            const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_COL, (uint32_t)k, 0);
+            const uint8_t v = yc[k] ? 1 : (u01(r.x) < (double)C);
+            c2 += v;
+            if (z_out) z_out[((size_t)blockIdx.x * (nyears + 1) + t + 1) * n + k] = v;
+            // zc is only read through yc in this phase, so it can be overwritten in place
+            zc[k] = v;
+        }
+        c2 = (int)(block_sum((double)c2, scratch) + 0.5);
+        if (tid == 0 && occ_out) occ_out[(size_t)blockIdx.x * (nyears + 1) + t + 1] = c2;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ peak probes (roofline denominators)
+__global__ void k_probe_mufu(float *out, int iters)
+{
+    float a = 0.5f + 1e-6f * threadIdx.x, b = 0.25f + 1e-6f * threadIdx.x, c = 0.125f, d = 0.75f;
+    for (int i = 0; i < iters; i++) {
+        a = Num<float>::ex2(-a); b = Num<float>::ex2(-b); c = Num<float>::ex2(-c); d = Num<float>::ex2(-d);
+    }
+    if (a + b + c + d == 12345.f) out[0] = a;
+}
+__global__ void k_probe_ffma(float *out, int iters)
+{
+    float a = 1.0f + threadIdx.x, b = 2.0f, c = 3.0f, d = 4.0f, e = 5.f, f = 6.f, g = 7.f, h = 8.f;
+    const float m = 0.999f, s = 1e-3f;
+    for (int i = 0; i < iters; i++) {
+        a = fmaf(a, m, s); b = fmaf(b, m, s); c = fmaf(c, m, s); d = fmaf(d, m, s);
+        e = fmaf(e, m, s); f = fmaf(f, m, s); g = fmaf(g, m, s); h = fmaf(h, m, s);
+    }
+    if (a + b + c + d + e + f + g + h == 12345.f) out[0] = a;
+}
+__global__ void k_probe_dadd(double *out, int iters)
+{
+    double a = 1.0 + threadIdx.x, b = 2.0, c = 3.0, d = 4.0, e = 5., f = 6., g = 7., h = 8.;
+    const double s = 1e-3;
+    for (int i = 0; i < iters; i++) { a += s; b += s; c += s; d += s; e += s; f += s; g += s; h += s; }
+    if (a + b + c + d + e + f + g + h == 12345.) out[0] = a;
+}
+__global__ void k_probe_copy(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+}  // namespace mp

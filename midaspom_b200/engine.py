@@ -1,0 +1,344 @@
+"""ctypes mirror of include/libmidaspom_cuda.h.
+
+``Engine`` wraps one ``mp_engine`` handle (one GPU).  Method names follow the C entry points
+(``mp_connectivity`` -> ``Engine.connectivity`` ...); arguments are numpy host arrays, exactly the
+flat buffers the C driver passes.  Every call raises ``MpError`` on a non-zero status; nothing here
+computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import build as _build
+
+FP32, FP64 = 0, 1
+GEOM_LINEAR, GEOM_COORDS, GEOM_DENSE = 0, 1, 2
+NDRAW, NLSIG, NPART = 8, 5, 4
+KERNEL_CATEGORIES = ("conn", "col", "sweep_y", "sweep_z", "small", "sim")
+DRAW_FIELDS = ("e", "c", "alpha", "b", "p", "loglik", "n_y1", "n_z1")
+
+# every symbol include/libmidaspom_cuda.h declares
+ABI_SYMBOLS = (
+    "mp_version", "mp_device_count", "mp_create", "mp_destroy", "mp_last_error",
+    "mp_set_landscape_linear", "mp_set_landscape_coords", "mp_set_landscape_dense", "mp_set_source_units",
+    "mp_set_observations", "mp_set_era", "mp_set_params", "mp_get_params", "mp_set_state", "mp_get_state",
+    "mp_set_scales", "mp_get_scales", "mp_connectivity", "mp_get_connectivity", "mp_loglik", "mp_loglik_host",
+    "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
+    "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
+    "mp_get_timing", "mp_probe_peaks", "mp_get_stream",
+)
+
+
+class MpError(RuntimeError):
+    pass
+
+
+class MpConfig(C.Structure):
+    _fields_ = [("n_patches", C.c_int32), ("n_years", C.c_int32), ("n_chains", C.c_int32), ("chain_offset", C.c_int32),
+                ("precision", C.c_int32), ("device", C.c_int32), ("detect", C.c_int32), ("max_draws", C.c_int32),
+                ("seed", C.c_uint64), ("prior_occ", C.c_double)]
+
+
+class MpParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("e", "c", "alpha", "b", "p", "K", "Ksrc", "dsrc")]
+
+
+class MpSamplerConfig(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("e_min", "e_max", "c_min", "c_max", "alpha_min", "alpha_max",
+                                          "b_min", "b_max", "p_min", "p_max")] + \
+               [(k, C.c_int32) for k in ("sample_e", "sample_c", "sample_alpha", "sample_b", "sample_p",
+                                         "n_e_steps", "n_c_steps", "n_adapt", "update_z", "update_y")]
+
+
+PARAM_FIELDS = ("e", "c", "alpha", "b", "p", "K", "Ksrc", "dsrc")
+PARAM_DEFAULTS = dict(e=0.5, c=0.5, alpha=1.0 / 400.0, b=0.0, p=1.0, K=1.0, Ksrc=0.0, dsrc=0.0)
+
+
+def sampler_config(**kw) -> MpSamplerConfig:
+    d = dict(e_min=0.0, e_max=1.0, c_min=0.0, c_max=1.0, alpha_min=1e-4, alpha_max=1e-1, b_min=0.0, b_max=2.0,
+             p_min=0.0, p_max=1.0, sample_e=1, sample_c=1, sample_alpha=0, sample_b=0, sample_p=0,
+             n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1)
+    d.update(kw)
+    return MpSamplerConfig(**d)
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen lib/libmidaspom_cuda.so (building it with nvcc if needed). Fails loudly if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.stale():
+        path = _build.build()
+    if not Path(path).exists():
+        raise MpError(f"{path} is missing: build it with `python -m midaspom_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(str(path))
+    vp, dp, u8p, i8p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int8)
+    pp, scp = C.POINTER(MpParams), C.POINTER(MpSamplerConfig)
+    L.mp_version.restype = C.c_char_p
+    L.mp_device_count.restype = C.c_int
+    L.mp_create.argtypes = [C.POINTER(MpConfig), C.POINTER(vp)]
+    L.mp_destroy.argtypes = [vp]
+    L.mp_last_error.argtypes = [vp]; L.mp_last_error.restype = C.c_char_p
+    L.mp_set_landscape_linear.argtypes = [vp, C.c_double, dp]
+    L.mp_set_landscape_coords.argtypes = [vp, dp, dp, dp]
+    L.mp_set_landscape_dense.argtypes = [vp, dp, dp]
+    L.mp_set_source_units.argtypes = [vp, dp]
+    L.mp_set_observations.argtypes = [vp, i8p]
+    L.mp_set_era.argtypes = [vp, u8p]
+    L.mp_set_params.argtypes = [vp, pp]; L.mp_get_params.argtypes = [vp, pp]
+    L.mp_set_state.argtypes = [vp, u8p, u8p]; L.mp_get_state.argtypes = [vp, u8p, u8p]
+    L.mp_set_scales.argtypes = [vp, dp]; L.mp_get_scales.argtypes = [vp, dp]
+    L.mp_connectivity.argtypes = [vp, dp]; L.mp_get_connectivity.argtypes = [vp, dp]
+    L.mp_loglik.argtypes = [vp, dp, dp]
+    L.mp_loglik_host.argtypes = [vp, pp, u8p, u8p, dp, dp]
+    L.mp_flip_delta.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+    L.mp_init_chains.argtypes = [vp, scp, C.c_int]
+    L.mp_set_sampler.argtypes = [vp, scp]
+    L.mp_sweep.argtypes = [vp, C.c_int]
+    L.mp_synchronize.argtypes = [vp]
+    L.mp_num_draws.argtypes = [vp]; L.mp_reset_draws.argtypes = [vp]; L.mp_sweep_index.argtypes = [vp]
+    L.mp_get_draws.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.mp_simulate.argtypes = [vp, pp, u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, u8p, C.POINTER(C.c_int32)]
+    L.mp_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mp_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.mp_set_timing.argtypes = [vp, C.c_int]
+    L.mp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
+    L.mp_probe_peaks.argtypes = [vp, dp]
+    _lib = L
+    return L
+
+
+def _p(a, ty):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+_dp, _u8p, _i8p = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int8)
+
+
+class Engine:
+    """One mp_engine handle: N patches x T years x C chains resident on one B200."""
+
+    def __init__(self, n_patches, n_years, n_chains=1, precision=FP64, device=0, seed=1, prior_occ=0.5, detect=0,
+                 chain_offset=0, max_draws=0):
+        self.lib = load_library()
+        self.cfg = MpConfig(n_patches, n_years, n_chains, chain_offset, precision, device, detect, max_draws, seed, prior_occ)
+        self.h = C.c_void_p()
+        rc = self.lib.mp_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.mp_last_error(None).decode()
+            self.h = None
+            raise MpError(f"mp_create failed ({rc}): {msg}")
+        self.N, self.T, self.C = n_patches, n_years, n_chains
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise MpError(f"{what} failed ({rc}): {self.lib.mp_last_error(self.h).decode()}")
+
+    # -- landscape / data
+    @staticmethod
+    def _f64(a, shape=None):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if shape is not None and a.shape != shape:
+            raise ValueError(f"expected shape {shape}, got {a.shape}")
+        return a
+
+    def set_landscape_linear(self, spacing, area=None):
+        area = self._f64(area, (self.N,))
+        self._ck(self.lib.mp_set_landscape_linear(self.h, float(spacing), _p(area, _dp)), "mp_set_landscape_linear")
+
+    def set_landscape_coords(self, x, y, area=None):
+        x, y, area = self._f64(x, (self.N,)), self._f64(y, (self.N,)), self._f64(area, (self.N,))
+        self._ck(self.lib.mp_set_landscape_coords(self.h, _p(x, _dp), _p(y, _dp), _p(area, _dp)), "mp_set_landscape_coords")
+
+    def set_landscape_dense(self, dist, area=None):
+        dist, area = self._f64(dist, (self.N, self.N)), self._f64(area, (self.N,))
+        self._ck(self.lib.mp_set_landscape_dense(self.h, _p(dist, _dp), _p(area, _dp)), "mp_set_landscape_dense")
+
+    def set_source_units(self, src_unit=None):
+        src_unit = self._f64(src_unit, (self.N,))
+        self._ck(self.lib.mp_set_source_units(self.h, _p(src_unit, _dp)), "mp_set_source_units")
+
+    def set_observations(self, obs):
+        obs = np.ascontiguousarray(obs, dtype=np.int8)
+        if obs.shape != (self.T, self.N):
+            raise ValueError(f"obs must be {(self.T, self.N)}")
+        self._ck(self.lib.mp_set_observations(self.h, _p(obs, _i8p)), "mp_set_observations")
+
+    def set_era(self, era=None):
+        era = None if era is None else np.ascontiguousarray(era, dtype=np.uint8)
+        if era is not None and era.shape != (self.T - 1,):
+            raise ValueError("era must have T-1 flags")
+        self._ck(self.lib.mp_set_era(self.h, _p(era, _u8p)), "mp_set_era")
+
+    # -- chain state
+    def _params_array(self, params):
+        arr = (MpParams * self.C)()
+        if isinstance(params, dict):
+            params = [params] * self.C
+        if len(params) != self.C:
+            raise ValueError("need one parameter set per chain")
+        for i, p in enumerate(params):
+            d = dict(PARAM_DEFAULTS)
+            if isinstance(p, dict):
+                d.update(p)
+            else:
+                d.update({k: getattr(p, k) for k in PARAM_FIELDS})
+            arr[i] = MpParams(*[float(d[k]) for k in PARAM_FIELDS])
+        return arr
+
+    def set_params(self, params):
+        self._ck(self.lib.mp_set_params(self.h, self._params_array(params)), "mp_set_params")
+
+    def get_params(self):
+        arr = (MpParams * self.C)()
+        self._ck(self.lib.mp_get_params(self.h, arr), "mp_get_params")
+        return [{k: getattr(arr[i], k) for k in PARAM_FIELDS} for i in range(self.C)]
+
+    def set_state(self, z, y):
+        z = np.ascontiguousarray(z, dtype=np.uint8).reshape(self.C, self.T, self.N)
+        y = np.ascontiguousarray(y, dtype=np.uint8).reshape(self.C, self.T - 1, self.N)
+        self._ck(self.lib.mp_set_state(self.h, _p(z, _u8p), _p(y, _u8p)), "mp_set_state")
+
+    def get_state(self):
+        z = np.zeros((self.C, self.T, self.N), dtype=np.uint8)
+        y = np.zeros((self.C, self.T - 1, self.N), dtype=np.uint8)
+        self._ck(self.lib.mp_get_state(self.h, _p(z, _u8p), _p(y, _u8p)), "mp_get_state")
+        return z, y
+
+    def set_scales(self, lsig):
+        lsig = np.ascontiguousarray(lsig, dtype=np.float64).reshape(self.C, NLSIG)
+        self._ck(self.lib.mp_set_scales(self.h, _p(lsig, _dp)), "mp_set_scales")
+
+    def get_scales(self):
+        lsig = np.zeros((self.C, NLSIG))
+        self._ck(self.lib.mp_get_scales(self.h, _p(lsig, _dp)), "mp_get_scales")
+        return lsig
+
+    # -- likelihood
+    def connectivity(self, fetch=True):
+        S = np.zeros((self.C, self.T - 1, self.N)) if fetch else None
+        self._ck(self.lib.mp_connectivity(self.h, _p(S, _dp)), "mp_connectivity")
+        return S
+
+    def get_connectivity(self):
+        S = np.zeros((self.C, self.T - 1, self.N))
+        self._ck(self.lib.mp_get_connectivity(self.h, _p(S, _dp)), "mp_get_connectivity")
+        return S
+
+    def loglik(self):
+        ll, parts = np.zeros(self.C), np.zeros((self.C, NPART))
+        self._ck(self.lib.mp_loglik(self.h, _p(ll, _dp), _p(parts, _dp)), "mp_loglik")
+        return ll, parts
+
+    def loglik_host(self, params, z, y):
+        z = np.ascontiguousarray(z, dtype=np.uint8).reshape(self.C, self.T, self.N)
+        y = np.ascontiguousarray(y, dtype=np.uint8).reshape(self.C, self.T - 1, self.N)
+        ll, parts = np.zeros(self.C), np.zeros((self.C, NPART))
+        self._ck(self.lib.mp_loglik_host(self.h, self._params_array(params), _p(z, _u8p), _p(y, _u8p), _p(ll, _dp),
+                                         _p(parts, _dp)), "mp_loglik_host")
+        return ll, parts
+
+    def flip_delta(self, chain, t, k):
+        out = C.c_double()
+        self._ck(self.lib.mp_flip_delta(self.h, chain, t, k, C.byref(out)), "mp_flip_delta")
+        return out.value
+
+    # -- sampler
+    def init_chains(self, sc: MpSamplerConfig, disperse=False):
+        self.sc = sc
+        self._ck(self.lib.mp_init_chains(self.h, C.byref(sc), int(disperse)), "mp_init_chains")
+
+    def set_sampler(self, sc: MpSamplerConfig):
+        self.sc = sc
+        self._ck(self.lib.mp_set_sampler(self.h, C.byref(sc)), "mp_set_sampler")
+
+    def sweep(self, nsweeps=1, sync=True):
+        self._ck(self.lib.mp_sweep(self.h, int(nsweeps)), "mp_sweep")
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        self._ck(self.lib.mp_synchronize(self.h), "mp_synchronize")
+
+    def num_draws(self):
+        return self.lib.mp_num_draws(self.h)
+
+    def reset_draws(self):
+        self._ck(self.lib.mp_reset_draws(self.h), "mp_reset_draws")
+
+    def get_draws(self, first=0, count=None):
+        if count is None:
+            count = self.num_draws() - first
+        out = np.zeros((count, self.C, NDRAW))
+        if count:
+            self._ck(self.lib.mp_get_draws(self.h, first, count, _p(out, _dp)), "mp_get_draws")
+        return out
+
+    # -- forward simulator
+    def simulate(self, params, z0, nyears, nsims=1, seed=1, era_all=False, want_states=True, want_counts=True):
+        par = self._one_param(params)
+        z0 = np.ascontiguousarray(z0, dtype=np.uint8)
+        z_out = np.zeros((nsims, nyears + 1, self.N), dtype=np.uint8) if want_states else None
+        occ = np.zeros((nsims, nyears + 1), dtype=np.int32) if want_counts else None
+        self._ck(self.lib.mp_simulate(self.h, C.byref(par), _p(z0, _u8p), nyears, nsims, seed, int(era_all),
+                                      _p(z_out, _u8p), _p(occ, C.POINTER(C.c_int32))), "mp_simulate")
+        return z_out, occ
+
+    @staticmethod
+    def _one_param(p):
+        d = dict(PARAM_DEFAULTS)
+        d.update(p if isinstance(p, dict) else {k: getattr(p, k) for k in PARAM_FIELDS})
+        return MpParams(*[float(d[k]) for k in PARAM_FIELDS])
+
+    # -- plumbing
+    def device_ptr(self, which):
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.mp_device_ptr(self.h, which, C.byref(ptr), C.byref(nbytes)), "mp_device_ptr")
+        return ptr.value, nbytes.value
+
+    def stream(self):
+        """Raw cudaStream_t of the engine (wrap with torch.cuda.ExternalStream for event timing)."""
+        st = C.c_void_p()
+        self._ck(self.lib.mp_get_stream(self.h, C.byref(st)), "mp_get_stream")
+        return st.value or 0
+
+    def set_timing(self, enabled=True):
+        self._ck(self.lib.mp_set_timing(self.h, int(enabled)), "mp_set_timing")
+
+    def get_timing(self, reset=False):
+        ms = np.zeros(len(KERNEL_CATEGORIES))
+        launches = np.zeros(len(KERNEL_CATEGORIES), dtype=np.int64)
+        self._ck(self.lib.mp_get_timing(self.h, _p(ms, _dp), _p(launches, C.POINTER(C.c_int64)), int(reset)), "mp_get_timing")
+        return dict(zip(KERNEL_CATEGORIES, ms.tolist())), dict(zip(KERNEL_CATEGORIES, launches.tolist()))
+
+    def probe_peaks(self):
+        out = np.zeros(4)
+        self._ck(self.lib.mp_probe_peaks(self.h, _p(out, _dp)), "mp_probe_peaks")
+        return dict(mufu_gops=out[0], ffma_gfma=out[1], dadd_gops=out[2], copy_gbs=out[3])

@@ -1,0 +1,69 @@
+"""Synthetic landscapes and occupancy histories of the shapes BASELINE.json names.
+
+Pure numpy (host side, not timed): uniform patch positions in a square of side sqrt(N)*250 m
+(seed 12345), lognormal(0, 0.5) areas (seed 12346), an occupancy history drawn from the model
+itself -- the generative step of the reference's simpij (main_MIDASPOM_future.c:64-110):
+survive iff u > E, colonise iff u < min(1, c*S) with S computed from the post-extinction state --
+then 5 % of the cells of years >= 1 set to -1 and, for imperfect detection, occupied cells reported
+as 0 with probability 1-p (Rscript/simuls_traj.R:107-133).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (N patches, T years, chains per GPU, imperfect detection)
+    "cfg2": dict(n=1000, T=10, chains_per_gpu=8, detect=1, desc="synthetic N=1,000 x T=10, 8 chains, imperfect detection"),
+    "cfg3": dict(n=10000, T=20, chains_per_gpu=8, detect=0, desc="synthetic N=10,000 x T=20, 64 chains over 8 GPUs (8 per GPU)"),
+    "tiny": dict(n=256, T=6, chains_per_gpu=4, detect=0, desc="smoke-test size"),
+}
+TRUTH = dict(e=0.3, alpha=1.0 / 400.0, b=0.5, p_detect=0.8, target_mean_C=0.3)
+
+
+def kernel_matrix(px, py, area, alpha, b, dtype=np.float32):
+    """W[l, k] = exp(-alpha d_lk) A_l^b, zero diagonal ([source][target], like M in main_MIDASPOM.c:180-188)."""
+    n = len(px)
+    W = np.empty((n, n), dtype=dtype)
+    aw = (area ** b).astype(dtype)
+    step = max(1, (1 << 24) // n)
+    for i in range(0, n, step):
+        d = np.sqrt((px[i:i + step, None] - px[None, :]) ** 2 + (py[i:i + step, None] - py[None, :]) ** 2)
+        W[i:i + step] = np.exp(-alpha * d).astype(dtype) * aw[i:i + step, None]
+    np.fill_diagonal(W, 0)
+    return W
+
+
+def make_workload(name: str, seed: int = 12345):
+    w = WORKLOADS[name]
+    n, T = w["n"], w["T"]
+    rng = np.random.default_rng(seed)
+    side = np.sqrt(n) * 250.0
+    px, py = rng.uniform(0, side, n), rng.uniform(0, side, n)
+    area = np.random.default_rng(seed + 1).lognormal(0.0, 0.5, n)
+    alpha, b, e = TRUTH["alpha"], TRUTH["b"], TRUTH["e"]
+    W = kernel_matrix(px, py, area, alpha, b)
+    z = np.zeros((T, n), dtype=np.uint8)
+    z[0] = rng.random(n) < 0.5
+    if not z[0].any():
+        z[0, 0] = 1
+    # c normalised so that the mean colonisation probability of the first transition is ~0.3
+    y0 = z[0] & (rng.random(n) > e)
+    S0 = y0.astype(np.float32) @ W
+    c = float(TRUTH["target_mean_C"] / max(S0.mean(), 1e-30))
+    y = y0
+    for t in range(T - 1):
+        if t > 0:
+            y = z[t] & (rng.random(n) > e)
+        S = y.astype(np.float32) @ W
+        C = np.minimum(1.0, c * S)
+        z[t + 1] = np.where(y == 1, 1, rng.random(n) < C)
+    obs = z.astype(np.int8)
+    if w["detect"]:
+        missed = (z == 1) & (rng.random(z.shape) > TRUTH["p_detect"])
+        obs[missed] = 0
+    hide = rng.random(z.shape) < 0.05
+    hide[0] = False
+    obs[hide] = -1
+    truth = dict(e=e, c=c, alpha=alpha, b=b, p=TRUTH["p_detect"] if w["detect"] else 1.0)
+    return dict(name=name, n=n, T=T, px=px, py=py, area=area, obs=obs, z_true=z, truth=truth, detect=w["detect"],
+                chains_per_gpu=w["chains_per_gpu"], desc=w["desc"])

@@ -6,9 +6,11 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
 /* Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3" (SC'11).  Not in the
@@ -63,16 +65,22 @@ static inline double pair_distance(const spom_model *m, int a, int b)
     }
 }
 /* main_MIDASPOM.c:184  M[i][j]=exp(-a*(j-i)*d)  -- evaluated as ((-a)*(j-i))*d */
-double spom_weight(const spom_model *m, double alpha, double b, int target, int source)
+static inline double dist_factor(const spom_model *m, double alpha, int target, int source)
 {
-    double w;
     if (m->geom == SPOM_GEOM_LINEAR) {
         const unsigned int gap = (unsigned int)abs(target - source);
-        w = exp(-alpha * gap * m->spacing);
-    } else {
-        w = exp(-alpha * pair_distance(m, target, source));
+        return exp(-alpha * gap * m->spacing);
     }
-    if (m->area && b != 0.0) w *= pow(m->area[source], b);
+    return exp(-alpha * pair_distance(m, target, source));
+}
+static inline double area_factor(const spom_model *m, double b, int source)
+{
+    return (m->area && b != 0.0) ? pow(m->area[source], b) : 1.0;
+}
+double spom_weight(const spom_model *m, double alpha, double b, int target, int source)
+{
+    double w = dist_factor(m, alpha, target, source);
+    if (m->area && b != 0.0) w *= area_factor(m, b, source);
     return w;
 }
 /* main_MIDASPOM.c:351-355  s1 += M[l][k]*piall[j][l], l ascending, l != k */
@@ -215,8 +223,37 @@ static double ll_det_counts(const spom_model *m, const spom_params *p, int64_t n
 
 void spom_refresh_S(const spom_model *m, const spom_params *par, const uint8_t *y, double *S)
 {
-    for (int t = 0; t + 1 < m->T; t++)
-        spom_connectivity(m, par->alpha, par->b, y + (size_t)t * m->n, S + (size_t)t * m->n);
+    /* S[t][k] = sum_{l != k, l ascending} w(k<-l) y[t][l]  (main_MIDASPOM.c:351-355 for every year);
+     * the weight of a pair is evaluated once and reused by every year -- same per-cell addition
+     * order as spom_connectivity, so the values are bit-identical to it. */
+    const int n = m->n, nt = m->T - 1;
+    uint8_t *any = calloc((size_t)n, 1);
+    for (int t = 0; t < nt; t++) for (int l = 0; l < n; l++) any[l] |= y[(size_t)t * n + l];
+    for (size_t i = 0; i < (size_t)nt * n; i++) S[i] = 0.0;
+    const int scaled = m->area && par->b != 0.0;
+    double *aw = malloc((size_t)n * sizeof(double));             /* A_l^b once per source: same value, same product */
+    for (int l = 0; l < n; l++) aw[l] = area_factor(m, par->b, l);
+    {
+        /* y as 0.0/1.0 doubles, years contiguous per source, and a contiguous accumulator per
+         * target: acc[t] += w * y01  adds exactly w or 0 (w*1 and w*0 are exact, also when fused),
+         * i.e. the same additions in the same order (l ascending) as the scalar reference loop,
+         * laid out so the compiler vectorises over t. */
+        double *yb = malloc((size_t)n * nt * sizeof(double)), *acc = malloc((size_t)(nt ? nt : 1) * sizeof(double));
+        for (int t = 0; t < nt; t++) for (int l = 0; l < n; l++) yb[(size_t)l * nt + t] = y[(size_t)t * n + l] ? 1.0 : 0.0;
+        for (int k = 0; k < n; k++) {
+            for (int t = 0; t < nt; t++) acc[t] = 0.0;
+            for (int l = 0; l < n; l++) {
+                if (l == k || !any[l]) continue;
+                double w = dist_factor(m, par->alpha, k, l);
+                if (scaled) w *= aw[l];
+                const double *yl = yb + (size_t)l * nt;
+                for (int t = 0; t < nt; t++) acc[t] += w * yl[t];
+            }
+            for (int t = 0; t < nt; t++) S[(size_t)t * n + k] = acc[t];
+        }
+        free(yb); free(acc);
+    }
+    free(any); free(aw);
 }
 
 double spom_loglik(const spom_model *m, const spom_params *p, const uint8_t *z, const uint8_t *y,
@@ -331,9 +368,12 @@ static double flip_eval(const spom_model *m, const spom_params *par, int t, int 
     const int nocc_after = *nocc + (cur ? -1 : 1);
     double acc = 0.0;
     (void)z_t;
+    const int scaled = m->area && par->b != 0.0;
+    const double awk = area_factor(m, par->b, k);
     for (int q = 0; q < n; q++) {
         if (q == k) { S_alt_buf[q] = S_t[q]; L_alt_buf[q] = 0.0; continue; }
-        const double w = spom_weight(m, par->alpha, par->b, q, k);
+        double w = dist_factor(m, par->alpha, q, k);
+        if (scaled) w *= awk;
         double sa = cur ? S_t[q] - w : S_t[q] + w;
         if (nocc_after == 0 || sa < 0.0) sa = 0.0;
         S_alt_buf[q] = sa;
@@ -401,14 +441,18 @@ void spom_init_chain(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t 
     spom_refresh_S(m, par, y, S);
 }
 
+/* Gibbs draws compare logit(u) with the log-odds: u < 1/(1+exp(-d))  <=>  log(u/(1-u)) < d */
+static inline double logit_u(uint32_t x) { const double u = spom_u01(x); return log(u) - log1p(-u); }
 static inline double adapt_gain(uint32_t sweep) { return 1.0 / pow((double)sweep + 1.0, 0.6); }
 static inline int mh_accept(double logu, double d) { if (isnan(d)) return 0; return logu < d; }
 
 int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t seed, uint32_t chain,
                    uint32_t sweep, spom_params *par, double *lsig, uint8_t *z, uint8_t *y, double *S,
-                   double *draw, int64_t y_flip_limit)
+                   double *draw, int64_t y_flip_limit, double *phase_s)
 {
     const int n = m->n, T = m->T;
+    const double t_begin = now_s();
+    double t_yscan = 0.0;
     const size_t cells = (size_t)(T - 1) * n;
     const int adapting = sweep < (uint32_t)cfg->n_adapt;
     const double gain = adapt_gain(sweep);
@@ -475,12 +519,12 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
                 if (t == 0) lo += log(p0) - log(1.0 - p0);
                 if (m->detect && m->obs[i] == 0) lo += log(1.0 - par->p);
                 spom_rng(seed, chain, sweep, RK_Z, (uint32_t)k, (uint32_t)t, r);
-                const double pz = isnan(lo) ? 0.0 : 1.0 / (1.0 + exp(-lo));
-                z[i] = spom_u01(r[0]) < pz;
+                z[i] = isnan(lo) ? 0 : (logit_u(r[0]) < lo);
             }
     }
     /* E: y_t | z -- systematic scan over candidate cells, rank-1 update of S_t */
     if (cfg->update_y) {
+        const double t_y0 = now_s();
         double *L = malloc((size_t)n * sizeof(double)), *sa = malloc((size_t)n * sizeof(double)),
                *la = malloc((size_t)n * sizeof(double));
         for (int t = 0; t + 1 < T; t++) {
@@ -501,8 +545,7 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
                 vis_t++;
                 const double d = flip_eval(m, par, t, k, z_t, z_n, y_t, S_t, L, &nocc, sa, la);
                 spom_rng(seed, chain, sweep, RK_Y, (uint32_t)k, (uint32_t)t, r);
-                const double pf = 1.0 / (1.0 + exp(-d));
-                if (spom_u01(r[0]) < pf) {
+                if (logit_u(r[0]) < d) {   /* u < sigmoid(d) */
                     const int cur = y_t[k];
                     memcpy(S_t, sa, (size_t)n * sizeof(double));
                     for (int q = 0; q < n; q++) if (q != k && !y_t[q]) L[q] = la[q];
@@ -516,6 +559,7 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
             visited += vis_t;
         }
         free(L); free(sa); free(la);
+        t_yscan = now_s() - t_y0;
     }
     /* C: random-walk MH on e from the sufficient counts */
     int64_t n10[2], n11[2], bad;
@@ -567,12 +611,13 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
                 + ll_det_counts(m, par, nd, nm, bad2);
         draw[6] = (double)sy; draw[7] = (double)sz;
     }
+    if (phase_s) { phase_s[0] = now_s() - t_begin - t_yscan; phase_s[1] = t_yscan; }
     return visited;
 }
 
 int64_t spom_sweep_chains(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t seed, int nchains,
                           uint32_t chain0, uint32_t sweep, spom_params *par, double *lsig, uint8_t *z,
-                          uint8_t *y, double *S, double *draws, int64_t y_flip_limit, int nthreads)
+                          uint8_t *y, double *S, double *draws, int64_t y_flip_limit, int nthreads, double *phase_s)
 {
     const size_t zc = (size_t)m->T * m->n, yc = (size_t)(m->T - 1) * m->n;
     int64_t total = 0;
@@ -583,7 +628,7 @@ int64_t spom_sweep_chains(const spom_model *m, const spom_sampler_cfg *cfg, uint
     for (int c = 0; c < nchains; c++)
         total += spom_sweep(m, cfg, seed, chain0 + (uint32_t)c, sweep, par + c, lsig + (size_t)c * SPOM_NLSIG,
                             z + c * zc, y + c * yc, S + c * yc, draws ? draws + (size_t)c * SPOM_NDRAW : NULL,
-                            y_flip_limit);
+                            y_flip_limit, phase_s ? phase_s + 2 * (size_t)c : NULL);
     return total;
 }
 int spom_max_threads(void)

@@ -99,7 +99,7 @@ void spom_refresh_S(const spom_model *m, const spom_params *par, const uint8_t *
  * (bounded sample for benchmarking); returns number of y candidates visited */
 int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t seed, uint32_t chain,
                    uint32_t sweep, spom_params *par, double *lsig, uint8_t *z, uint8_t *y, double *S,
-                   double *draw, int64_t y_flip_limit);
+                   double *draw, int64_t y_flip_limit, double *phase_s /* nullable: [other, y scan] seconds */);
 /* rank-1 incremental log-odds of flipping y[t][k] given a consistent S (what the sweep uses) */
 double spom_flip_delta(const spom_model *m, const spom_params *par, const uint8_t *z, const uint8_t *y,
                        const double *S, int t, int k);
@@ -111,7 +111,8 @@ void spom_simulate(const spom_model *m, const spom_params *p, uint64_t seed, uin
 /* ---- multi-chain helpers for the CPU baseline (OpenMP over chains) ---- */
 int64_t spom_sweep_chains(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t seed, int nchains,
                           uint32_t chain0, uint32_t sweep, spom_params *par, double *lsig, uint8_t *z,
-                          uint8_t *y, double *S, double *draws, int64_t y_flip_limit, int nthreads);
+                          uint8_t *y, double *S, double *draws, int64_t y_flip_limit, int nthreads,
+                          double *phase_s /* nullable: nchains x [other, y scan] seconds */);
 int spom_max_threads(void);
 
 #ifdef __cplusplus

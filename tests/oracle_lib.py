@@ -80,10 +80,10 @@ def lib() -> C.CDLL:
         L.spom_flip_delta.restype = C.c_double
         L.spom_init_chain.argtypes = [mp, cp, C.c_uint64, C.c_uint32, C.c_int, pp, _dp, _u8p, _u8p, _dp]
         L.spom_refresh_S.argtypes = [mp, pp, _u8p, _dp]
-        L.spom_sweep.argtypes = [mp, cp, C.c_uint64, C.c_uint32, C.c_uint32, pp, _dp, _u8p, _u8p, _dp, _dp, C.c_int64]
+        L.spom_sweep.argtypes = [mp, cp, C.c_uint64, C.c_uint32, C.c_uint32, pp, _dp, _u8p, _u8p, _dp, _dp, C.c_int64, _dp]
         L.spom_sweep.restype = C.c_int64
         L.spom_sweep_chains.argtypes = [mp, cp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, pp, _dp, _u8p, _u8p,
-                                        _dp, _dp, C.c_int64, C.c_int]
+                                        _dp, _dp, C.c_int64, C.c_int, _dp]
         L.spom_sweep_chains.restype = C.c_int64
         L.spom_max_threads.restype = C.c_int
         L.spom_simulate.argtypes = [mp, pp, C.c_uint64, C.c_uint32, _u8p, C.c_int, _u8p]
@@ -197,11 +197,12 @@ class Chains:
     def run(self, nsweeps: int, y_flip_limit: int = -1, nthreads: int = 0):
         out = np.zeros((nsweeps, self.nchains, NDRAW))
         visited = 0
+        self.phase_s = np.zeros((self.nchains, 2))           # last sweep: [everything else, y scan] seconds per chain
         for s in range(nsweeps):
             visited += lib().spom_sweep_chains(self.m.ref(), C.byref(self.cfg), self.seed, self.nchains, self.chain0,
                                                self.sweep, self.par, _ptr(self.lsig, _dp), _ptr(self.z, _u8p),
                                                _ptr(self.y, _u8p), _ptr(self.S, _dp), _ptr(self.draws, _dp),
-                                               y_flip_limit, nthreads)
+                                               y_flip_limit, nthreads, _ptr(self.phase_s, _dp))
             out[s] = self.draws
             self.sweep += 1
         self.visited = visited

@@ -1,0 +1,352 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (libmidaspom_cuda.so), against the
+CPU oracle on the same seeded inputs, the committed golden fixtures, and size-independent
+properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): log-likelihood and connectivity within 1e-9 relative on
+the FP64 path and 1e-5 on the FP32 path; latent-state indexing and bookkeeping bit-exact."""
+import numpy as np
+import pytest
+
+import midaspom_b200 as mb
+import oracle_lib as O
+from gpu_util import make_engine, make_model, pdict, oparams, random_landscape
+from stats_util import grid_marginals, grid_moments, ess, ks_distance_thinned, rhat
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {mb.FP64: 1e-9, mb.FP32: 1e-5}
+A = 1.0 / 400
+
+
+def rel_close(got, want, rtol, floor=1e-300):
+    got, want = np.asarray(got, float), np.asarray(want, float)
+    both_inf = np.isneginf(got) & np.isneginf(want)
+    ok = both_inf | (np.abs(got - want) <= rtol * np.maximum(np.abs(want), floor))
+    assert ok.all(), f"max rel err {np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), floor)):.3e} > {rtol}"
+
+
+def oracle_S(m, par, y):
+    return np.array([O.connectivity(m, par["alpha"], par["b"], y[t]) for t in range(y.shape[0])])
+
+
+# ------------------------------------------------------------------ connectivity (a2)
+@pytest.mark.parametrize("precision", [mb.FP64, mb.FP32])
+def test_connectivity_bundled_example_every_state(golden, precision):
+    """S for all 256 enumerated states of the bundled example == main_MIDASPOM.c:351-355."""
+    piall = golden["cpp_piall"].astype(np.uint8)            # 256 x 8
+    n = piall.shape[1]
+    spec = dict(obs=np.zeros((2, n), dtype=np.int8), spacing=100.0)
+    m = make_model(spec)
+    C = piall.shape[0]
+    with make_engine(spec, n_chains=C, precision=precision) as eng:
+        eng.set_params([pdict(alpha=A)] * C)
+        eng.set_state(np.zeros((C, 2, n), np.uint8), piall[:, None, :])
+        S = eng.connectivity()
+    want = np.array([O.connectivity(m, A, 0.0, piall[j]) for j in range(C)])
+    rel_close(S[:, 0, :], want, 1e-14 if precision == mb.FP64 else 1e-5, floor=1e-12)
+    assert (S[0] == 0).all()                                 # empty landscape: exactly zero
+
+
+@pytest.mark.parametrize("precision", [mb.FP64, mb.FP32])
+@pytest.mark.parametrize("geom", [O.GEOM_LINEAR, O.GEOM_COORDS, O.GEOM_DENSE])
+def test_connectivity_random_landscapes(precision, geom):
+    rng = np.random.default_rng(100 + geom)
+    n, T, C = 517, 11, 3                                      # ragged: not a multiple of the 128-wide tile
+    spec, z, y = random_landscape(rng, n, T, geom)
+    m = make_model(spec)
+    pars = [pdict(alpha=1 / 300, b=0.0), pdict(alpha=1 / 500, b=0.5), pdict(alpha=1 / 150, b=1.3)]
+    ys = np.stack([y, np.roll(y, 1, axis=1), np.zeros_like(y)])
+    with make_engine(spec, n_chains=C, precision=precision) as eng:
+        eng.set_params(pars)
+        eng.set_state(np.stack([z] * C), ys)
+        S = eng.connectivity()
+    for c in range(C):
+        rel_close(S[c], oracle_S(m, pars[c], ys[c]), RTOL[precision], floor=1e-6)
+    assert (S[2] == 0).all()
+
+
+def test_connectivity_more_than_32_years():
+    rng = np.random.default_rng(5)
+    spec, z, y = random_landscape(rng, 70, 41, O.GEOM_COORDS)
+    m = make_model(spec)
+    par = pdict(alpha=1 / 400, b=0.4)
+    with make_engine(spec, precision=mb.FP64) as eng:
+        eng.set_params([par]); eng.set_state(z[None], y[None])
+        rel_close(eng.connectivity()[0], oracle_S(m, par, y), 1e-12, floor=1e-9)
+
+
+# ------------------------------------------------------------------ log-likelihood (a3, a4, a8)
+CASES = [
+    ("base", dict(), pdict(e=0.31, c=0.012, alpha=1 / 400)),
+    ("areas", dict(), pdict(e=0.55, c=0.02, alpha=1 / 250, b=0.8)),
+    ("dieoff", dict(era=True), pdict(e=0.4, c=0.01, alpha=1 / 400, K=2.5)),
+    ("loss", dict(era=True), pdict(e=0.4, c=0.01, alpha=1 / 400, K=1.0, Ksrc=3.0, dsrc=35.0)),
+    ("future", dict(era=True), pdict(e=0.9, c=0.015, alpha=1 / 300, K=1.7, Ksrc=0.8, dsrc=50.0, b=0.3)),
+    ("detect", dict(detect=1), pdict(e=0.3, c=0.02, alpha=1 / 400, p=0.8)),
+    ("clampE", dict(), pdict(e=1.4, c=0.02, alpha=1 / 400)),
+]
+
+
+@pytest.mark.parametrize("precision", [mb.FP64, mb.FP32])
+@pytest.mark.parametrize("geom", [O.GEOM_LINEAR, O.GEOM_COORDS])
+@pytest.mark.parametrize("name,extra,par", CASES, ids=[c[0] for c in CASES])
+def test_loglik_parts_vs_oracle(precision, geom, name, extra, par):
+    rng = np.random.default_rng(sum(map(ord, name)) + geom)
+    n, T = 300, 9
+    spec, z, y = random_landscape(rng, n, T, geom, miss=0.05 if name != "detect" else 0.0)
+    if extra.get("era"):
+        spec["era"] = (np.arange(T - 1) < 4).astype(np.uint8)
+    if extra.get("detect"):
+        spec["detect"] = 1
+        obs = z.astype(np.int8)
+        obs[(z == 1) & (rng.random(z.shape) < 0.2)] = 0      # missed detections
+        spec["obs"] = obs
+    if name == "clampE":
+        y[:] = 0                                              # E = 1: every occupied patch goes extinct
+    m = make_model(spec)
+    want, parts = O.loglik(m, oparams(par), z, y)
+    with make_engine(spec, precision=precision) as eng:
+        ll, gparts = eng.loglik_host([par], z[None], y[None])
+    rel_close(gparts[0], parts, RTOL[precision], floor=1.0)
+    rel_close(ll[0], want, RTOL[precision], floor=1.0)
+
+
+def test_loglik_impossible_states_are_minus_infinity():
+    """Where the reference returns probability 0 (compPePc:34-37,46-47) the engine returns -inf."""
+    n, T = 16, 3
+    obs = np.zeros((T, n), np.int8); obs[:, :8] = 1
+    spec = dict(obs=obs, spacing=100.0)
+    z = (obs == 1).astype(np.uint8)
+    y_ok = (z[:-1] & z[1:]).astype(np.uint8)
+    par = pdict(e=0.3, c=0.5, alpha=A)
+    bad_y0 = y_ok.copy(); bad_y0[0, 12] = 1                   # y=1 where z_t=0
+    z_bad = z.copy(); z_bad[1, 3] = 0                         # contradicts obs=1 under perfect detection
+    y_none = np.zeros_like(y_ok)                              # nobody survives but patches occupied next year: C=0
+    y_forced = y_ok.copy(); z2 = z.copy(); z2[2, 0] = 0       # y=1 but z'=0
+    with make_engine(spec, n_chains=4) as eng:
+        ll, parts = eng.loglik_host([par] * 4, np.stack([z, z_bad, z, z2]), np.stack([bad_y0, y_ok, y_none, y_forced]))
+    assert np.isneginf(ll).all()
+    m = make_model(spec)
+    for zz, yy in ((z, bad_y0), (z_bad, y_ok), (z, y_none), (z2, y_forced)):
+        assert np.isneginf(O.loglik(m, oparams(par), zz, yy)[0])
+    zc = z.copy()                                             # clamp C=1 with z'=0 => log(1-1)
+    spec2 = dict(obs=zc.astype(np.int8), spacing=100.0)
+    with make_engine(spec2) as eng:
+        ll, _ = eng.loglik_host([pdict(e=0.3, c=50.0, alpha=A)], zc[None], (zc[:-1] & zc[1:])[None])
+        assert np.isneginf(ll[0])
+
+
+def test_loglik_bundled_example_complete_data_terms(golden, example_obs):
+    """Complete-data log-likelihood on the bundled example for every completion of its 3 missing
+    cells, y = all survivors: engine == oracle (which is pinned to compPePc)."""
+    T, n = example_obs.shape
+    miss = np.argwhere(example_obs == -1)
+    zs, ys = [], []
+    for mask in range(2 ** len(miss)):
+        z = (example_obs == 1).astype(np.uint8)
+        for b, (t, k) in enumerate(miss):
+            z[t, k] = (mask >> b) & 1
+        zs.append(z); ys.append(z[:-1] & z[1:])
+    spec = dict(obs=example_obs, spacing=100.0, prior_occ=0.5)
+    m = make_model(spec)
+    par = pdict(e=0.71, c=0.52, alpha=A)
+    with make_engine(spec, n_chains=len(zs)) as eng:
+        ll, parts = eng.loglik_host([par] * len(zs), np.stack(zs), np.stack(ys))
+    want = [O.loglik(m, oparams(par), z, y)[0] for z, y in zip(zs, ys)]
+    rel_close(ll, want, 1e-12, floor=1.0)
+
+
+# ------------------------------------------------------------------ rank-1 flips
+@pytest.mark.parametrize("precision", [mb.FP64, mb.FP32])
+@pytest.mark.parametrize("geom", [O.GEOM_LINEAR, O.GEOM_COORDS, O.GEOM_DENSE])
+def test_flip_delta_vs_oracle(precision, geom):
+    rng = np.random.default_rng(40 + geom)
+    n, T = 200, 6
+    spec, z, y = random_landscape(rng, n, T, geom)
+    spec["era"] = np.array([1, 1, 0, 0, 0], dtype=np.uint8)
+    m = make_model(spec)
+    par = pdict(e=0.35, c=0.015, alpha=1 / 450, b=0.6, K=1.8, Ksrc=0.5, dsrc=30.0)
+    cand = np.argwhere((z[:-1] & z[1:]) == 1)
+    pick = cand[rng.choice(len(cand), 12, replace=False)]
+    with make_engine(spec, precision=precision) as eng:
+        eng.set_params([par]); eng.set_state(z[None], y[None])
+        S = eng.connectivity()[0]
+        got = [eng.flip_delta(0, int(t), int(k)) for t, k in pick]
+    want = [O.flip_delta_bruteforce(m, oparams(par), z, y, int(t), int(k)) for t, k in pick]
+    tol = 1e-9 if precision == mb.FP64 else 2e-4               # sum of ~200 FP32 log differences
+    for g, w in zip(got, want):
+        assert abs(g - w) <= tol * max(1.0, abs(w))
+
+
+# ------------------------------------------------------------------ sampler: draw-by-draw twin
+@pytest.mark.parametrize("geom,detect,sample_ab", [(O.GEOM_LINEAR, 0, 0), (O.GEOM_COORDS, 0, 1), (O.GEOM_COORDS, 1, 1)])
+def test_fp64_sweeps_follow_the_cpu_twin(geom, detect, sample_ab):
+    """Same Philox counters, same scan order: after k sweeps the FP64 engine and the oracle twin
+    hold IDENTICAL latent states (bit-exact bookkeeping) and parameters equal to rounding."""
+    rng = np.random.default_rng(77 + geom + detect)
+    n, T, C = 90, 7, 3
+    spec, z, _ = random_landscape(rng, n, T, geom, occ=0.5, miss=0.08, areas=bool(sample_ab))
+    if detect:
+        spec["detect"] = 1
+    m = make_model(spec)
+    kw = dict(sample_alpha=sample_ab, sample_b=sample_ab, sample_p=detect, alpha_min=1e-4, alpha_max=5e-2,
+              c_max=1.0, n_adapt=10, n_c_steps=2)
+    par0 = pdict(e=0.4, c=0.03, alpha=1 / 400, b=0.5 if sample_ab else 0.0, p=0.8 if detect else 1.0)
+    seed = 1234
+    ch = O.Chains(m, O.sampler_cfg(**kw), C, seed=seed, par0=oparams(par0), disperse=True)
+    nsw = 12
+    want = ch.run(nsw)
+    with make_engine(spec, n_chains=C, seed=seed, max_draws=nsw) as eng:
+        eng.set_params([par0] * C)
+        eng.init_chains(mb.engine.sampler_config(**kw), disperse=True)
+        eng.sweep(nsw)
+        got = eng.get_draws()
+        zg, yg = eng.get_state()
+        Sg = eng.get_connectivity()
+    assert (zg == ch.z).all() and (yg == ch.y).all()
+    assert (got[:, :, 6:] == want[:, :, 6:]).all()               # counts of y=1 and z=1, every sweep
+    rel_close(got[:, :, :5], want[:, :, :5], 1e-9)
+    rel_close(got[:, :, 5], want[:, :, 5], 1e-9, floor=1.0)
+    rel_close(Sg, ch.S, 1e-9, floor=1e-9)
+
+
+def test_chain_offset_selects_the_stream():
+    """A chain's random stream depends on its GLOBAL id only: chains [2,3] run alone reproduce
+    chains 2,3 of a 4-chain engine (the property MIDASPOM_MPI's row split relies on, :361-372)."""
+    rng = np.random.default_rng(9)
+    spec, z, _ = random_landscape(rng, 64, 6, O.GEOM_COORDS, miss=0.1, areas=False)
+    sc = mb.engine.sampler_config(n_adapt=5)
+    outs = []
+    for C, off in ((4, 0), (2, 2)):
+        with make_engine(spec, n_chains=C, seed=7, max_draws=8, chain_offset=off, precision=mb.FP32) as eng:
+            eng.set_params([pdict(e=0.4, c=0.03)] * C)
+            eng.init_chains(sc, disperse=True)
+            eng.sweep(8)
+            outs.append((eng.get_draws(), eng.get_state()))
+    assert (outs[0][0][:, 2:, :] == outs[1][0]).all()
+    assert (outs[0][1][1][2:] == outs[1][1][1]).all()
+
+
+# ------------------------------------------------------------------ sampler: posterior vs the reference's exact grid
+def test_fp32_sampler_posterior_matches_reference_grid(golden, example_obs):
+    """BASELINE north_star: posterior agreement is statistical.  (e, c) draws of the FP32 engine on
+    the bundled example vs the exact 101x101 posterior written by MIDASPOM.out (run_examples.sh:8)."""
+    spec = dict(obs=example_obs, spacing=100.0, prior_occ=0.5)
+    C, nsw, burn = 8, 12000, 1000
+    with make_engine(spec, n_chains=C, precision=mb.FP32, seed=99, max_draws=nsw) as eng:
+        eng.set_params([pdict(alpha=A)] * C)
+        eng.init_chains(mb.engine.sampler_config(n_adapt=500, n_c_steps=2), disperse=True)
+        eng.sweep(nsw)
+        d = eng.get_draws()[burn:]
+    grid, pe, pc, w = grid_marginals(golden["post_default"])
+    for col, pm in ((0, pe), (1, pc)):
+        mean, sd = grid_moments(grid, pm)
+        x = d[:, :, col]
+        n_eff = sum(ess(x[:, i]) for i in range(C))
+        assert abs(x.mean() - mean) < 5 * sd / np.sqrt(n_eff) + 2e-3
+        assert abs(x.std() - sd) < 0.06 * sd
+        assert rhat(x) < 1.02
+        lo, hi = np.quantile(x, [0.025, 0.975])
+        cdf = np.cumsum(pm)
+        glo, ghi = grid[np.searchsorted(cdf, 0.025)], grid[np.searchsorted(cdf, 0.975)]
+        assert abs(lo - glo) < 0.03 and abs(hi - ghi) < 0.03     # 95% CIs overlap to within 3 grid steps
+        thin = max(1, int(np.ceil(x.size / n_eff)) * 2)
+        dist, nn = ks_distance_thinned(x.T.ravel(), grid, pm, thin)
+        assert dist < 1.63 / np.sqrt(nn) + 0.01
+
+
+# ------------------------------------------------------------------ forward simulator (a9)
+@pytest.mark.parametrize("geom", [O.GEOM_LINEAR, O.GEOM_COORDS])
+def test_simulator_follows_the_cpu_twin(geom):
+    rng = np.random.default_rng(21)
+    n, years, nsims = 50, 12, 6
+    spec, z, _ = random_landscape(rng, n, 2, geom, areas=True)
+    par = pdict(e=0.5, c=0.05, alpha=1 / 500, b=0.4, K=1.5, Ksrc=0.7, dsrc=60.0)
+    spec_o = dict(spec); spec_o["era"] = np.ones(years, dtype=np.uint8)
+    m = make_model(spec_o)
+    with make_engine(spec, precision=mb.FP64) as eng:
+        zs, occ = eng.simulate(par, z[0], years, nsims=nsims, seed=5, era_all=True)
+    for s in range(nsims):
+        want = O.simulate(m, oparams(par), 5, s, z[0], years)
+        assert (zs[s] == want).all()
+        assert (occ[s] == want.sum(axis=1)).all()
+
+
+def test_simulator_one_step_distribution_matches_simpij(golden):
+    """Occupancy frequencies after one year vs 10,000 draws of the reference's simpij (libc rand)."""
+    z0 = golden["simpij_z0"].astype(np.uint8)
+    e, c, K, Ks, a, d, ds = golden["simpij_pars"]
+    spec = dict(obs=np.zeros((2, len(z0)), np.int8), spacing=d)
+    nsim = 40000
+    with make_engine(spec, precision=mb.FP32) as eng:
+        zs, _ = eng.simulate(pdict(e=e, c=c, alpha=a, K=K, Ksrc=Ks, dsrc=ds), z0, 1, nsims=nsim, seed=3, era_all=True)
+    freq = zs[:, 1, :].mean(axis=0)
+    ref = golden["simpij_freq"]
+    se = np.sqrt(ref * (1 - ref) * (1 / nsim + 1 / int(golden["simpij_nsim"])))
+    assert (np.abs(freq - ref) < 4.5 * se + 1e-9).all()
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_shapes():
+    """Single patch, two years, all-missing rows, N not a multiple of any tile."""
+    for n, T in ((1, 2), (2, 2), (33, 3), (129, 2)):
+        rng = np.random.default_rng(n)
+        spec, z, y = random_landscape(rng, n, T, O.GEOM_LINEAR, areas=False)
+        spec["obs"][1:] = -1                                   # later years entirely unobserved
+        m = make_model(spec)
+        par = pdict(e=0.4, c=0.3, alpha=A)
+        with make_engine(spec, max_draws=4) as eng:
+            ll, _ = eng.loglik_host([par], z[None], y[None])
+            rel_close(ll[0], O.loglik(m, oparams(par), z, y)[0], 1e-10, floor=1.0)
+            eng.set_params([par])
+            eng.init_chains(mb.engine.sampler_config(n_adapt=2), disperse=False)
+            eng.sweep(4)
+            zg, yg = eng.get_state()
+            assert ((yg[0] <= zg[0][:-1]) & (yg[0] <= zg[0][1:])).all()
+            assert (zg[0][0] == (spec["obs"][0] == 1)).all() or (spec["obs"][0] == -1).any()
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE cfg3 shape)
+def test_full_size_properties_cfg3():
+    """N=10,000 x T=20 (cfg3 shape), FP32 engine: connectivity is linear in y, the rank-1 log-odds
+    equals the difference of two full evaluations, and after a sweep the incrementally updated S
+    equals a from-scratch recomputation while the state stays feasible."""
+    rng = np.random.default_rng(12345)
+    n, T, C = 10000, 20, 2
+    spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.4, miss=0.05, areas=True)
+    par = pdict(e=0.3, c=0.004, alpha=1 / 400, b=0.5)
+    with make_engine(spec, n_chains=C, precision=mb.FP32, max_draws=2, seed=3) as eng:
+        eng.set_params([par] * C)
+        ya = y * (rng.random(y.shape) < 0.5)
+        yb = y - ya
+        eng.set_state(np.stack([z, z]), np.stack([ya, yb]))
+        Sab = eng.connectivity()
+        eng.set_state(np.stack([z, z]), np.stack([y, np.zeros_like(y)]))
+        Sy = eng.connectivity()
+        rel_close(Sab[0] + Sab[1], Sy[0], 1e-12, floor=1e-9)   # linearity: FP64 accumulation of identical weights
+        assert (Sy[1] == 0).all()
+        t, k = 7, int(np.flatnonzero(z[7] & z[8])[5])
+        delta32 = eng.flip_delta(0, t, k)
+        with make_engine(spec, n_chains=2, precision=mb.FP64) as e64:
+            y2 = y.copy(); y2[t, k] ^= 1
+            e64.set_params([par] * 2)
+            e64.set_state(np.stack([z, z]), np.stack([y, y2]))
+            ll, _ = e64.loglik()
+            delta64 = e64.flip_delta(0, t, k)
+        assert abs((ll[1] - ll[0]) - delta64) < 1e-6           # rank-1 form == difference of full sums
+        assert abs(delta32 - delta64) < 1e-3 * max(1.0, abs(delta64))
+        # a sweep keeps everything consistent
+        eng.set_state(np.stack([z, z]), np.stack([y, y]))
+        eng.init_chains(mb.engine.sampler_config(sample_alpha=1, sample_b=1, alpha_min=1e-4, alpha_max=1e-1,
+                                                 c_max=0.1, n_adapt=2), disperse=False)
+        eng.sweep(2)
+        zg, yg = eng.get_state()
+        S_inc = eng.get_connectivity()
+        S_new = eng.connectivity()
+        rel_close(S_inc, S_new, 1e-9, floor=1e-9)
+        obs = spec["obs"]
+        for c in range(C):
+            assert ((yg[c] <= zg[c][:-1]) & (yg[c] <= zg[c][1:])).all()
+            assert (zg[c][obs == 1] == 1).all() and (zg[c][obs == 0] == 0).all()
+        d = eng.get_draws()
+        assert np.isfinite(d[:, :, 5]).all()
