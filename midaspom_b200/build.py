@@ -4,17 +4,20 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
+OBJ_DIR = LIB_DIR / "obj"
 LIB = LIB_DIR / "libmidaspom_cuda.so"
-SOURCES = [CSRC / "mp_engine.cu"]
-HEADERS = [CSRC / "mp_device.cuh", CSRC / "mp_kernels.cuh", PKG.parent / "include" / "libmidaspom_cuda.h"]
+SOURCES = [CSRC / "mp_engine.cu", CSRC / "mp_sweep_fast_linear.cu", CSRC / "mp_sweep_fast_coords.cu",
+           CSRC / "mp_sweep_fast_dense.cu"]
+HEADERS = [CSRC / "mp_device.cuh", CSRC / "mp_kernels.cuh", CSRC / "mp_sweep_fast.cuh", CSRC / "mp_host.h",
+           PKG.parent / "include" / "libmidaspom_cuda.h"]
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def nvcc() -> str:
@@ -31,17 +34,27 @@ def stale() -> bool:
     return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
 
 
+def _compile(src: Path, verbose: bool):
+    obj = OBJ_DIR / (src.stem + ".o")
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", str(obj), str(src)]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ))
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src.name}:\n{res.stdout}{res.stderr}")
+    return obj, res.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
-    LIB_DIR.mkdir(exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(s) for s in SOURCES]
-    env = dict(os.environ)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+    cmd = [nvcc(), "-shared", "-o", str(LIB)] + [str(o) for o, _ in results]
+    res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        (LIB_DIR / "ptxas.log").write_text("".join(log for _, log in results))
     return LIB
 
 

@@ -85,20 +85,44 @@ template <typename R> struct Landscape {
     const double *src_unit;    // nullable => k+1
 };
 
-// distance-dependent factor exp(-alpha d(target, source)); the area factor A_source^b is applied by the caller
+// Dispersal weight of a (target, source) pair, w = A_source^b exp(-alpha d(target, source)).
+// The two per-chain / per-source constants are passed pre-transformed so that EVERY kernel of a
+// precision evaluates the identical expression (a weight added by one kernel and removed by
+// another must cancel exactly):
+//   FP64: apre = alpha,            awv = A^b        w = exp(-(alpha d)) * A^b        (oracle order)
+//   FP32: apre = -alpha log2(e),   awv = log2(A^b)  w = ex2(fma(apre, d, awv))        (one FFMA + MUFU.EX2)
+template <typename R> __device__ __forceinline__ R alpha_pre(double alpha);
+template <> __device__ __forceinline__ double alpha_pre<double>(double alpha) { return alpha; }
+template <> __device__ __forceinline__ float alpha_pre<float>(double alpha) { return -1.4426950408889634f * (float)alpha; }
+template <typename R> __device__ __forceinline__ R area_pre(double aw);
+template <> __device__ __forceinline__ double area_pre<double>(double aw) { return aw; }
+template <> __device__ __forceinline__ float area_pre<float>(double aw) { return (float)log2(aw); }
+
+__device__ __forceinline__ double weight_of(double apre, double awv, double d) { return exp(-(apre * d)) * awv; }
+__device__ __forceinline__ float weight_of(float apre, float awv, float d) { return Num<float>::ex2(fmaf(apre, d, awv)); }
+
 template <typename R, int GEOM>
-__device__ __forceinline__ R kernel_factor(const Landscape<R> &ls, R alpha, int target, int source, R tx, R ty, R sx, R sy)
+__device__ __forceinline__ R pair_distance(const Landscape<R> &ls, int target, int source, R tx, R ty, R sx, R sy)
 {
     if (GEOM == MP_GEOM_LINEAR) {
         const int gap = target > source ? target - source : source - target;
-        // reference order: exp(((-a)*(j-i))*d)  (main_MIDASPOM.c:184)
-        return Num<R>::exp_neg((alpha * (R)gap) * ls.spacing);
+        return (R)gap * ls.spacing;
     } else if (GEOM == MP_GEOM_COORDS) {
         const R dx = tx - sx, dy = ty - sy;
-        return Num<R>::exp_neg(alpha * Num<R>::sqrtv(dx * dx + dy * dy));
+        return Num<R>::sqrtv(fma(dx, dx, dy * dy));      // explicit FMA: identical in every kernel
     } else {
-        return Num<R>::exp_neg(alpha * ls.dist[(size_t)source * ls.n + target]);
+        return ls.dist[(size_t)source * ls.n + target];
     }
+}
+// reference order for the linear geometry in FP64: exp(((-a)*(j-i))*d)  (main_MIDASPOM.c:184)
+template <typename R, int GEOM>
+__device__ __forceinline__ R pair_weight(const Landscape<R> &ls, R apre, R awv, int target, int source, R tx, R ty, R sx, R sy)
+{
+    if (GEOM == MP_GEOM_LINEAR && sizeof(R) == 8) {
+        const int gap = target > source ? target - source : source - target;
+        return (R)(exp(-((double)apre * (double)gap) * (double)ls.spacing) * (double)awv);
+    }
+    return weight_of(apre, awv, pair_distance<R, GEOM>(ls, target, source, tx, ty, sx, sy));
 }
 
 // per-chain derived constants of one transition

@@ -1,120 +1,14 @@
 // mp_engine.cu -- host side of libmidaspom_cuda.so: the engine handle, device memory, kernel
 // launch sequences and the extern "C" entry points declared in include/libmidaspom_cuda.h.
 // No CPU fallback: without a usable sm_100 device every entry point returns MP_ERR_CUDA.
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
+#include "mp_host.h"
 #include "mp_kernels.cuh"
+#include "mp_sweep_fast.cuh"   // k_build_candidates, CandRec
 
 using namespace mp;
 
 static thread_local std::string g_create_error;
 
-struct mp_engine {
-    mp_config cfg{};
-    mp_sampler_config sc{};
-    bool have_sc = false, have_landscape = false, have_obs = false, have_state = false;
-    int geom = MP_GEOM_LINEAR;
-    bool have_area = false;
-    double spacing = 100.0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-
-    // landscape
-    double *d_area = nullptr, *d_src_unit = nullptr;
-    void *d_px = nullptr, *d_py = nullptr, *d_dist = nullptr;   // float or double per cfg.precision
-    // data
-    int8_t *d_obs = nullptr;
-    uint8_t *d_era = nullptr;
-    bool have_era = false;
-    // chains
-    mp_params *d_par = nullptr, *d_prop = nullptr;
-    double *d_lsig = nullptr;
-    uint8_t *d_z = nullptr, *d_y = nullptr;
-    uint32_t *d_ybits = nullptr;
-    int nwords = 1;
-    double *d_S[2] = { nullptr, nullptr };
-    void *d_aw[2] = { nullptr, nullptr };
-    double *d_partial[2] = { nullptr, nullptr };
-    double *d_llc = nullptr, *d_logu = nullptr, *d_parts = nullptr, *d_scalar = nullptr;
-    int *d_flags = nullptr;
-    unsigned long long *d_counts = nullptr;
-    double *d_draws = nullptr;
-    int ndraws = 0;
-    uint32_t sweep = 0;
-    int nblk_col = 1;
-    // timing
-    bool timing = false;
-    struct Span { cudaEvent_t a, b; int cat; };
-    std::vector<Span> spans;
-    std::vector<cudaEvent_t> pool;
-    double t_ms[MP_K_NCAT] = { 0 };
-    long long t_launch[MP_K_NCAT] = { 0 };
-};
-
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess) {                                                                         \
-            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
-            return MP_ERR_CUDA;                                                                          \
-        }                                                                                                \
-    } while (0)
-#define REQUIRE(cond, code, msg)                                                                         \
-    do { if (!(cond)) { h->err = (msg); return (code); } } while (0)
-
-static inline size_t nN(const mp_engine *h) { return (size_t)h->cfg.n_patches; }
-static inline size_t nT(const mp_engine *h) { return (size_t)h->cfg.n_years; }
-static inline size_t nC(const mp_engine *h) { return (size_t)h->cfg.n_chains; }
-static inline size_t zcells(const mp_engine *h) { return nT(h) * nN(h); }
-static inline size_t ycells(const mp_engine *h) { return (nT(h) - 1) * nN(h); }
-static inline bool is64(const mp_engine *h) { return h->cfg.precision == MP_FP64; }
-static inline size_t rsz(const mp_engine *h) { return is64(h) ? sizeof(double) : sizeof(float); }
-
-// ---- timing spans: CUDA events on the engine stream around every launch of a category
-struct Timed {
-    mp_engine *h; int cat; cudaEvent_t a = nullptr, b = nullptr;
-    Timed(mp_engine *h_, int cat_) : h(h_), cat(cat_)
-    {
-        h->t_launch[cat]++;
-        if (!h->timing) return;
-        a = take(); b = take();
-        cudaEventRecord(a, h->stream);
-    }
-    ~Timed()
-    {
-        if (!h->timing) return;
-        cudaEventRecord(b, h->stream);
-        h->spans.push_back({ a, b, cat });
-    }
-    cudaEvent_t take()
-    {
-        if (!h->pool.empty()) { cudaEvent_t e = h->pool.back(); h->pool.pop_back(); return e; }
-        cudaEvent_t e; cudaEventCreate(&e); return e;
-    }
-};
-static void drain_spans(mp_engine *h)
-{
-    for (auto &s : h->spans) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) h->t_ms[s.cat] += ms;
-        h->pool.push_back(s.a); h->pool.push_back(s.b);
-    }
-    h->spans.clear();
-}
-
-template <typename R> static Landscape<R> view(const mp_engine *h)
-{
-    Landscape<R> ls;
-    ls.n = h->cfg.n_patches; ls.spacing = (R)h->spacing;
-    ls.px = (const R *)h->d_px; ls.py = (const R *)h->d_py; ls.dist = (const R *)h->d_dist;
-    ls.src_unit = h->d_src_unit;
-    return ls;
-}
 static SamplerDev sampler_dev(const mp_engine *h)
 {
     SamplerDev sd;
@@ -208,8 +102,44 @@ template <typename R, int GEOM> static int launch_sweep_y_g(mp_engine *h)
     CK(cudaGetLastError());
     return MP_OK;
 }
+// ---- FP32 fast path (mp_sweep_fast.cuh; kernels live in mp_sweep_fast_{linear,coords,dense}.cu)
+static int pick_cluster(int tasks, int sms, int max_cs)
+{
+    // split each task over CS CTAs so that tasks*CS fills the SMs evenly; ties -> smaller CS
+    int best = 1; double best_cost = 1e30;
+    for (int cs = 1; cs <= max_cs; cs *= 2) {
+        const int ctas = tasks * cs;
+        const double cost = (double)((ctas + sms - 1) / sms) / cs * (1.0 + 0.02 * cs);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = cs; }
+    }
+    return best;
+}
+static bool fast_sweep_ok(const mp_engine *h)
+{
+    return !is64(h) && !(h->have_era && h->any_src) && h->cfg.n_patches <= 31 * 1024;
+}
+static int launch_sweep_y_fast(mp_engine *h)
+{
+    const int n = h->cfg.n_patches, ntrans = h->cfg.n_years - 1, C = h->cfg.n_chains;
+    {
+        Timed tm(h, MP_K_SMALL);
+        k_build_candidates<<<C * ntrans, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
+                                                                (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
+                                                                h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS);
+        CK(cudaGetLastError());
+    }
+    Timed tm(h, MP_K_SWEEP_Y);
+    const int ept = (n + 1023) / 1024;                 // targets per thread (1024 threads per task)
+    const int cs = pick_cluster(C * ntrans, h->sm_count, 8);
+    switch (h->geom) {
+    case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, ept, cs);
+    case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, ept, cs);
+    default: return mp_launch_sweep_fast_dense(h, ept, cs);
+    }
+}
 template <typename R> static int launch_sweep_y(mp_engine *h)
 {
+    if (fast_sweep_ok(h)) return launch_sweep_y_fast(h);
     const size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
     REQUIRE(smem <= 227 * 1024, MP_ERR_UNSUPPORTED, "n_patches too large for the shared-memory resident y sweep");
     switch (h->geom) {
@@ -337,7 +267,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -368,6 +298,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     }
     mp_engine *h = new mp_engine();
     h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char *what, cudaError_t ce) {
         g_create_error = std::string("mp_create: ") + what + ": " + cudaGetErrorString(ce);
         mp_destroy(h);
@@ -392,6 +323,8 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_scalar, 64 }, { (void **)&h->d_flags, C * 4 * sizeof(int) },
         { (void **)&h->d_counts, C * NCOUNT * sizeof(unsigned long long) },
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
+        { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
+        { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) },
     };
     for (auto &r : reqs) {
         if ((e = cudaMalloc(r.p, r.bytes)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -497,6 +430,8 @@ int mp_set_params(mp_engine *h, const mp_params *par)
     if (!h || !par) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
     for (size_t c = 0; c < nC(h); c++) REQUIRE(par[c].K > 0.0 && par[c].alpha > 0.0, MP_ERR_ARG, "need K > 0 and alpha > 0");
+    h->any_src = false;
+    for (size_t c = 0; c < nC(h); c++) if (par[c].Ksrc != 0.0) h->any_src = true;
     CK(cudaMemcpyAsync(h->d_par, par, nC(h) * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return MP_OK;

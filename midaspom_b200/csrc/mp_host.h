@@ -1,0 +1,125 @@
+// mp_host.h -- host-side engine state shared by the translation units of libmidaspom_cuda.so.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include "../../include/libmidaspom_cuda.h"
+#include "mp_device.cuh"
+
+
+struct mp_engine {
+    mp_config cfg{};
+    mp_sampler_config sc{};
+    bool have_sc = false, have_landscape = false, have_obs = false, have_state = false;
+    int geom = MP_GEOM_LINEAR;
+    bool have_area = false;
+    double spacing = 100.0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // landscape
+    double *d_area = nullptr, *d_src_unit = nullptr;
+    void *d_px = nullptr, *d_py = nullptr, *d_dist = nullptr;   // float or double per cfg.precision
+    // data
+    int8_t *d_obs = nullptr;
+    uint8_t *d_era = nullptr;
+    bool have_era = false;
+    // chains
+    mp_params *d_par = nullptr, *d_prop = nullptr;
+    double *d_lsig = nullptr;
+    uint8_t *d_z = nullptr, *d_y = nullptr;
+    uint32_t *d_ybits = nullptr;
+    int nwords = 1;
+    double *d_S[2] = { nullptr, nullptr };
+    void *d_aw[2] = { nullptr, nullptr };
+    double *d_partial[2] = { nullptr, nullptr };
+    double *d_llc = nullptr, *d_logu = nullptr, *d_parts = nullptr, *d_scalar = nullptr;
+    int *d_flags = nullptr;
+    unsigned long long *d_counts = nullptr;
+    double *d_draws = nullptr;
+    int ndraws = 0;
+    uint32_t sweep = 0;
+    int nblk_col = 1;
+    void *d_cand = nullptr;          // candidate records of the FP32 fast sweep (mp::CandRec, 32 B each)
+    int *d_cand_count = nullptr;     // [task][2]: candidates, occupied
+    bool any_src = false;            // some chain has an external source term (Ksrc != 0)
+    int sm_count = 148;
+    // timing
+    bool timing = false;
+    struct Span { cudaEvent_t a, b; int cat; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    double t_ms[MP_K_NCAT] = { 0 };
+    long long t_launch[MP_K_NCAT] = { 0 };
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return MP_ERR_CUDA;                                                                          \
+        }                                                                                                \
+    } while (0)
+#define REQUIRE(cond, code, msg)                                                                         \
+    do { if (!(cond)) { h->err = (msg); return (code); } } while (0)
+
+inline size_t nN(const mp_engine *h) { return (size_t)h->cfg.n_patches; }
+inline size_t nT(const mp_engine *h) { return (size_t)h->cfg.n_years; }
+inline size_t nC(const mp_engine *h) { return (size_t)h->cfg.n_chains; }
+inline size_t zcells(const mp_engine *h) { return nT(h) * nN(h); }
+inline size_t ycells(const mp_engine *h) { return (nT(h) - 1) * nN(h); }
+inline bool is64(const mp_engine *h) { return h->cfg.precision == MP_FP64; }
+inline size_t rsz(const mp_engine *h) { return is64(h) ? sizeof(double) : sizeof(float); }
+
+// ---- timing spans: CUDA events on the engine stream around every launch of a category
+struct Timed {
+    mp_engine *h; int cat; cudaEvent_t a = nullptr, b = nullptr;
+    Timed(mp_engine *h_, int cat_) : h(h_), cat(cat_)
+    {
+        h->t_launch[cat]++;
+        if (!h->timing) return;
+        a = take(); b = take();
+        cudaEventRecord(a, h->stream);
+    }
+    ~Timed()
+    {
+        if (!h->timing) return;
+        cudaEventRecord(b, h->stream);
+        h->spans.push_back({ a, b, cat });
+    }
+    cudaEvent_t take()
+    {
+        if (!h->pool.empty()) { cudaEvent_t e = h->pool.back(); h->pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+inline void drain_spans(mp_engine *h)
+{
+    for (auto &s : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) h->t_ms[s.cat] += ms;
+        h->pool.push_back(s.a); h->pool.push_back(s.b);
+    }
+    h->spans.clear();
+}
+
+template <typename R> inline mp::Landscape<R> view(const mp_engine *h)
+{
+    mp::Landscape<R> ls;
+    ls.n = h->cfg.n_patches; ls.spacing = (R)h->spacing;
+    ls.px = (const R *)h->d_px; ls.py = (const R *)h->d_py; ls.dist = (const R *)h->d_dist;
+    ls.src_unit = h->d_src_unit;
+    return ls;
+}
+
+
+// FP32 fast sweep (mp_sweep_fast_*.cu, one translation unit per geometry)
+int mp_launch_sweep_fast_linear(mp_engine *h, int ept, int cs);
+int mp_launch_sweep_fast_coords(mp_engine *h, int ept, int cs);
+int mp_launch_sweep_fast_dense(mp_engine *h, int ept, int cs);

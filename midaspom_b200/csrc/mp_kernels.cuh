@@ -1,7 +1,7 @@
 // mp_kernels.cuh -- the CUDA kernels of the SPOM engine (sm_100a).  Included by mp_engine.cu only.
 //
 //  k_pack_y        y bytes -> one 32-year bit word per (chain, patch)      (feeds k_conn)
-//  k_area_weights  aw[set][chain][l] = A_l^b
+//  k_area_weights  aw[set][chain][l] = A_l^b (FP64) or log2 A_l^b (FP32), see pair_weight
 //  k_conn          fused on-the-fly dispersal-kernel x occupancy contraction  (main_MIDASPOM.c:350-358)
 //  k_col_ll        colonisation log-terms + per-chain segmented reduction      (compPePc:40,44)
 //  k_counts        integer bookkeeping: extinction / detection / prior counts  (compPePc:38-39)
@@ -44,7 +44,7 @@ __global__ void k_area_weights(const mp_params *__restrict__ par, const double *
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n) return;
     const double b = par[c].b;
-    aw[(size_t)c * n + l] = (area && b != 0.0) ? (R)pow(area[l], b) : (R)1;
+    aw[(size_t)c * n + l] = area_pre<R>((area && b != 0.0) ? pow(area[l], b) : 1.0);
 }
 
 // ------------------------------------------------------------------ connectivity
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
     __shared__ uint32_t sbits[CONN_TILE];
     const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
     const int k = blockIdx.x * CONN_TILE + tid;
-    const R alpha = (R)a.par[set][c].alpha;
+    const R apre = alpha_pre<R>(a.par[set][c].alpha);
     const R *aw = a.aw[set] + (size_t)c * n;
     R tx = 0, ty = 0;
     if (GEOM == MP_GEOM_COORDS && k < n) { tx = a.ls.px[k]; ty = a.ls.py[k]; }
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
                 for (int j = 0; j < CONN_TILE; j++) {
                     const uint32_t bits = sbits[j];
                     if (bits == 0 || l0 + j == k) continue;       // l != k  (main_MIDASPOM.c:354)
-                    const R wgt = saw[j] * kernel_factor<R, GEOM>(a.ls, alpha, k, l0 + j, tx, ty, sx[j], sy[j]);
+                    const R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], k, l0 + j, tx, ty, sx[j], sy[j]);
                     const double wd = (double)wgt;
 #pragma unroll
                     for (int t = 0; t < NYB; t++) if (bits & (1u << t)) acc[t] += wd;
@@ -402,7 +402,7 @@ __device__ __forceinline__ R flip_pair(const Landscape<R> &ls, const Trans<R> &t
 {
     R qx = 0, qy = 0;
     if (GEOM == MP_GEOM_COORDS) { qx = ls.px[q]; qy = ls.py[q]; }
-    const R w = awk * kernel_factor<R, GEOM>(ls, tr.alpha, q, k, qx, qy, kx, ky);
+    const R w = pair_weight<R, GEOM>(ls, alpha_pre<R>((double)tr.alpha), awk, q, k, qx, qy, kx, ky);
     double sa = cur ? Sq - (double)w : Sq + (double)w;
     if (zero_after || sa < 0.0) sa = 0.0;
     S_alt = sa;
@@ -569,9 +569,8 @@ __global__ void k_simulate(Landscape<R> ls, mp_params p, const double *__restric
                 if (l == k || !yc[l]) continue;
                 R lx = 0, ly = 0;
                 if (GEOM == MP_GEOM_COORDS) { lx = ls.px[l]; ly = ls.py[l]; }
-                R w = kernel_factor<R, GEOM>(ls, tr.alpha, k, l, kx, ky, lx, ly);
-                if (area && p.b != 0.0) w *= (R)pow(area[l], p.b);
-                s += (double)w;
+                const R awl = area_pre<R>((area && p.b != 0.0) ? pow(area[l], p.b) : 1.0);
+                s += (double)pair_weight<R, GEOM>(ls, alpha_pre<R>(p.alpha), awl, k, l, kx, ky, lx, ly);
             }
             const R C = col_prob<R>(tr, (R)s, source_term<R>(ls, tr, k));
             const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_COL, (uint32_t)k, 0);

@@ -1,0 +1,5 @@
+// FP32 fast y sweep, coords geometry (see mp_sweep_fast.cuh); separate TU so the geometries compile in parallel.
+#include "../../include/libmidaspom_cuda.h"
+#define MP_FAST_GEOM MP_GEOM_COORDS
+#include "mp_sweep_fast.cuh"
+int mp_launch_sweep_fast_coords(mp_engine *h, int ept, int cs) { return mp::launch_fast_any(h, ept, cs); }

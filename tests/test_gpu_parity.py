@@ -210,6 +210,39 @@ def test_fp64_sweeps_follow_the_cpu_twin(geom, detect, sample_ab):
     rel_close(Sg, ch.S, 1e-9, floor=1e-9)
 
 
+@pytest.mark.parametrize("geom,n,C,T", [(O.GEOM_COORDS, 700, 3, 6), (O.GEOM_LINEAR, 2100, 2, 4), (O.GEOM_DENSE, 300, 5, 5),
+                                         (O.GEOM_COORDS, 1500, 19, 9)])
+def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T):
+    """The FP32 throughput sweep (cluster-split, two-float S, product-of-factors logs) draws from the
+    same thresholds as the FP64 path: after one sweep from the same state the latent states agree
+    except where a log-odds lies within FP32 rounding of its threshold, S agrees to 1e-5, and the
+    incrementally updated S equals a fresh recomputation (rank-1 bookkeeping)."""
+    rng = np.random.default_rng(500 + n)
+    spec, z, y = random_landscape(rng, n, T, geom, occ=0.5, miss=0.05)
+    par = pdict(e=0.35, c=0.02 if geom != O.GEOM_LINEAR else 0.2, alpha=1 / 400, b=0.5)
+    sc = mb.engine.sampler_config(sample_e=0, sample_c=0, update_z=0, n_adapt=0)
+    out = {}
+    for prec in (mb.FP64, mb.FP32):
+        with make_engine(spec, n_chains=C, precision=prec, seed=11, max_draws=1) as eng:
+            eng.set_params([par] * C)
+            eng.set_state(np.stack([z] * C), np.stack([y] * C))
+            eng.set_sampler(sc)
+            eng.connectivity(fetch=False)
+            eng.sweep(1)
+            zz, yy = eng.get_state()
+            S_inc = eng.get_connectivity()
+            S_new = eng.connectivity()
+            out[prec] = (yy, S_inc, S_new)
+    y64, S64, _ = out[mb.FP64]
+    y32, S32, S32new = out[mb.FP32]
+    cand = ((z[:-1] & z[1:]) == 1).sum() * C
+    assert (y64 != y32).sum() <= max(2, 2e-3 * cand)
+    assert ((y32 <= z[None, :-1]) & (y32 <= z[None, 1:])).all()
+    rel_close(S32, S32new, 1e-6, floor=1e-9)                     # two-float rank-1 updates vs from scratch
+    same = (y64 == y32).all(axis=2)                               # years whose states coincide: S must agree
+    rel_close(S32[same], S64[same], 1e-5, floor=1e-9)
+
+
 def test_chain_offset_selects_the_stream():
     """A chain's random stream depends on its GLOBAL id only: chains [2,3] run alone reproduce
     chains 2,3 of a 4-chain engine (the property MIDASPOM_MPI's row split relies on, :361-372)."""
