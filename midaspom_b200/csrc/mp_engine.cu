@@ -46,7 +46,7 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int nsets
     a.aw[0] = (const R *)h->d_aw[0]; a.aw[1] = (const R *)h->d_aw[1];
     a.S[0] = h->d_S[0]; a.S[1] = h->d_S[1];
     a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords;
-    dim3 grid((h->cfg.n_patches + CONN_TILE - 1) / CONN_TILE, h->cfg.n_chains, nsets);
+    dim3 grid((h->cfg.n_patches + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
     const int ny = a.ntrans;
     if (ny <= 8) k_conn<R, GEOM, 8><<<grid, CONN_TILE, 0, h->stream>>>(a);
     else if (ny <= 16) k_conn<R, GEOM, 16><<<grid, CONN_TILE, 0, h->stream>>>(a);

@@ -15,7 +15,8 @@
 
 namespace mp {
 
-constexpr int CONN_TILE = 128;      // targets per CTA == sources per shared-memory tile
+constexpr int CONN_TILE = 128;      // threads per CTA == sources per shared-memory tile
+constexpr int CONN_TGT = 2;         // targets per thread (register blocking of the year contraction)
 constexpr int COL_THREADS = 256;
 constexpr int MAX_COL_BLOCKS = 64;  // partial sums per chain (fixed => deterministic reduction order)
 constexpr int NCOUNT = 12;          // per-chain integer counters, see k_counts
@@ -65,43 +66,77 @@ template <typename R> struct ConnArgs {
 template <typename R, int GEOM, int NYB>
 __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
 {
+    // Each thread owns CONN_TGT targets (k, k + 128, ...) and NYB year accumulators per target.
+    // Per source of the tile: coordinates, area constant, and the year bits expanded to 0.0 / 1.0
+    // doubles, so that the contraction over years is a chain of DFMAs
+    //   acc[t] = fma(w, y01[t], acc[t])   (== acc[t] + w or acc[t], exactly)
+    // fed by broadcast LDS.128; the y01 loads are shared by the CONN_TGT targets of the thread.
     __shared__ R sx[CONN_TILE], sy[CONN_TILE], saw[CONN_TILE];
     __shared__ uint32_t sbits[CONN_TILE];
+    __shared__ __align__(16) double sy01[CONN_TILE][NYB];
     const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
-    const int k = blockIdx.x * CONN_TILE + tid;
-    const R apre = alpha_pre<R>(a.par[set][c].alpha);
-    const R *aw = a.aw[set] + (size_t)c * n;
-    R tx = 0, ty = 0;
-    if (GEOM == MP_GEOM_COORDS && k < n) { tx = a.ls.px[k]; ty = a.ls.py[k]; }
+    const int kbase = blockIdx.x * CONN_TILE * CONN_TGT + tid;
+    const mp_params *parp = set ? a.par[1] : a.par[0];
+    const R apre = alpha_pre<R>(parp[c].alpha);
+    const R *aw = (set ? a.aw[1] : a.aw[0]) + (size_t)c * n;
+    double *Sout = (set ? a.S[1] : a.S[0]) + (size_t)c * a.ntrans * n;
+    R tx[CONN_TGT], ty[CONN_TGT];
+#pragma unroll
+    for (int g = 0; g < CONN_TGT; g++) {
+        const int k = kbase + g * CONN_TILE;
+        tx[g] = 0; ty[g] = 0;
+        if (GEOM == MP_GEOM_COORDS && k < n) { tx[g] = a.ls.px[k]; ty[g] = a.ls.py[k]; }
+    }
     for (int w = 0; w < a.nwords; w++) {
         const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
-        double acc[NYB];
+        double acc[CONN_TGT][NYB];
 #pragma unroll
-        for (int t = 0; t < NYB; t++) acc[t] = 0.0;
+        for (int g = 0; g < CONN_TGT; g++)
+#pragma unroll
+            for (int t = 0; t < NYB; t++) acc[g][t] = 0.0;
         for (int l0 = 0; l0 < n; l0 += CONN_TILE) {
             const int l = l0 + tid;
+            uint32_t bits = 0;
             if (l < n) {
                 if (GEOM == MP_GEOM_COORDS) { sx[tid] = a.ls.px[l]; sy[tid] = a.ls.py[l]; }
-                saw[tid] = aw[l]; sbits[tid] = bw[l];
-            } else sbits[tid] = 0;
-            __syncthreads();
-            if (k < n) {
-#pragma unroll 4
-                for (int j = 0; j < CONN_TILE; j++) {
-                    const uint32_t bits = sbits[j];
-                    if (bits == 0 || l0 + j == k) continue;       // l != k  (main_MIDASPOM.c:354)
-                    const R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], k, l0 + j, tx, ty, sx[j], sy[j]);
-                    const double wd = (double)wgt;
+                saw[tid] = aw[l]; bits = bw[l];
+            }
+            sbits[tid] = bits;
 #pragma unroll
-                    for (int t = 0; t < NYB; t++) if (bits & (1u << t)) acc[t] += wd;
+            for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
+            __syncthreads();
+            if (kbase < n) {
+                for (int j = 0; j < CONN_TILE; j++) {
+                    if (sbits[j] == 0) continue;                       // tile-uniform: source empty in every year
+                    double wd[CONN_TGT];
+#pragma unroll
+                    for (int g = 0; g < CONN_TGT; g++) {
+                        const int k = kbase + g * CONN_TILE;
+                        R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], k, l0 + j, tx[g], ty[g], sx[j], sy[j]);
+                        if (l0 + j == k) wgt = 0;                       // l != k  (main_MIDASPOM.c:354)
+                        wd[g] = (double)wgt;
+                    }
+                    const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
+#pragma unroll
+                    for (int t2 = 0; t2 < NYB / 2; t2++) {
+                        const double2 m = yb[t2];
+#pragma unroll
+                        for (int g = 0; g < CONN_TGT; g++) {
+                            acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
+                            acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
+                        }
+                    }
                 }
             }
             __syncthreads();
         }
-        if (k < n) {
-            double *S = a.S[set] + (size_t)c * a.ntrans * n;
 #pragma unroll
-            for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) S[(size_t)(32 * w + t) * n + k] = acc[t];
+        for (int g = 0; g < CONN_TGT; g++) {
+            const int k = kbase + g * CONN_TILE;
+            if (k < n) {
+#pragma unroll
+                for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = acc[g][t];
+            }
         }
     }
 }

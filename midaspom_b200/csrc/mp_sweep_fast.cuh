@@ -290,20 +290,33 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         }
         const float delta = 0.6931471805599453f * total;
         if (thr_k < delta) {                              // NaN compares false: no flip
-            for (int j = 0; j < ept; j++) {
-                if (j == kj) continue;                   // S_k does not contain y_k
-                const float4 tq = sT[tid + j * NT];
-                const float a = sgn * fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * 1024, tq.z, tq.w, drow);
-                const float s = tq.x + a, bb = s - tq.x;
-                const float e = (tq.x - (s - bb)) + (a - bb);       // exact rounding error of hi + a
-                const float lo2 = tq.y + e;
-                float hi = s + lo2, lo = lo2 - (hi - s);
-                if (zero_after || hi < 0.f) { hi = 0.f; lo = 0.f; }
-                *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
-            }
             if (own) { ybits ^= ownbit; Amask ^= ownbit; }  // cur=1 -> y=0 joins class A ; cur=0 -> leaves it
             nocc += cur ? -1 : 1;
-            D = refresh_D();
+            // commit: S +- w for every own target (two-float), and the new denominator D in the same pass
+            float Dn = 0.f, P = 1.f;
+            auto commit_one = [&](int j) {
+                const float4 tq = sT[tid + j * NT];
+                float hi = tq.x;
+                if (j != kj) {                           // S_k does not contain y_k
+                    const float a = sgn * fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * 1024, tq.z, tq.w, drow);
+                    const float s = tq.x + a, bb = s - tq.x;
+                    const float e = (tq.x - (s - bb)) + (a - bb);   // exact rounding error of hi + a
+                    const float lo2 = tq.y + e;
+                    hi = s + lo2;
+                    float lo = lo2 - (hi - s);
+                    if (zero_after || hi < 0.f) { hi = 0.f; lo = 0.f; }
+                    *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
+                }
+                P *= col_factor(cK, hi, (Amask >> j) & 1u, (Bmask >> j) & 1u);
+            };
+            int j = 0;
+            for (; j + U <= ept; j += U) {
+#pragma unroll
+                for (int u = 0; u < U; u++) commit_one(j + u);
+                Dn += Num<float>::lg2(P); P = 1.f;
+            }
+            if (j < ept) { for (; j < ept; j++) commit_one(j); Dn += Num<float>::lg2(P); }
+            D = Dn;
         }
         r0 = n0; r1 = n1;
     }
