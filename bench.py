@@ -248,13 +248,22 @@ def run_ours(args, rank, local_rank, world):
         n_sweepy = max(1, klaunch["sweep_y"])
         t_sweepy = kms["sweep_y"] / n_sweepy * 1e-3                           # s per launch (CUDA events, engine stream)
         pairs = cpg * ncand * (n - 1)                                         # pair evaluations per launch
-        mufu_per_pair = 3                                                     # sqrt + ex2 + lg2 (planar geometry)
-        alg_bytes = cpg * (T - 1) * n * (8 + 1 + 1 + 1 + 8 + 1)               # read S,y,z_t,z_t+1 ; write S,y
+        mufu_per_pair = 2.2                                                   # MUFU.SQRT + MUFU.EX2 + MUFU.LG2 / 5 (planar geometry)
+        alg_bytes = cpg * (T - 1) * n * (8 + 1 + 1 + 1 + 8 + 1) + cpg * ncand * 32   # S,y,z_t,z_t+1 in; S,y out; candidate records
         t_conn = kms["conn"] / max(1, klaunch["conn"]) * 1e-3
         conn_pairs = cpg * 2 * float(n) * n                                   # current + proposal parameter sets
-        roof = dict(bound="sfu", kernel="k_sweep_y", achieved=pairs * mufu_per_pair / t_sweepy * 1e-9,
+        traffic = None                                                        # dram read+write per launch, from the tracked ncu summary
+        for f in sorted((ROOT / "profiles").glob("*_ncu_full.json"), reverse=True):
+            for kd in json.loads(f.read_text()):
+                if "k_sweep_y_fast" in kd.get("kernel", "") and "dram_traffic_bytes_per_launch" in kd:
+                    traffic = dict(bytes_per_launch=kd["dram_traffic_bytes_per_launch"], source=f"profiles/{f.name}")
+                    break
+            if traffic:
+                break
+        roof = dict(bound="sfu", kernel="k_sweep_y_fast", achieved=pairs * mufu_per_pair / t_sweepy * 1e-9,
                     peak=probe["mufu_gops"], unit="Gop/s (MUFU)", frac=pairs * mufu_per_pair / t_sweepy * 1e-9 / probe["mufu_gops"],
-                    traffic=None, share_of_step=kms["sweep_y"] / max(total_ms, 1e-9), ms_per_launch=t_sweepy * 1e3,
+                    traffic=traffic, share_of_step=kms["sweep_y"] / max(total_ms, 1e-9), ms_per_launch=t_sweepy * 1e3,
+                    algorithmic=dict(pairs_per_launch=pairs, mufu_per_pair=mufu_per_pair, bytes_per_launch=alg_bytes),
                     peak_source="mp_probe_peaks micro-benchmark on this GPU (MEASURED_PEAKS.json has no MUFU figure)",
                     hbm=dict(achieved=alg_bytes / t_sweepy * 1e-9, peak=hbm_peak, unit="GB/s", frac=alg_bytes / t_sweepy * 1e-9 / hbm_peak,
                              peak_source="MEASURED_PEAKS.json" if peaks_meas else "fallback"),

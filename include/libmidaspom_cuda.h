@@ -131,6 +131,20 @@ int mp_sweep_index(mp_engine *h);
  * year (future.c).  z_out (nullable): nsims*(nyears+1)*N ; occupied_out (nullable): nsims*(nyears+1) counts */
 int mp_simulate(mp_engine *h, const mp_params *par, const uint8_t *z0, int nyears, int nsims, uint64_t seed,
                 int era_all, uint8_t *z_out, int32_t *occupied_out);
+/* same, with one parameter set and one start state per trajectory (future.c:359-381 draws (e,c) from
+ * the posterior table and a completion of the last survey for every simulation) */
+int mp_simulate_ensemble(mp_engine *h, const mp_params *par_per_sim /* nsims */, const uint8_t *z0_per_sim /* nsims*N */,
+                         int nyears, int nsims, uint64_t seed, int era_all, uint8_t *z_out, int32_t *occupied_out);
+
+/* ---- exact small-n engine: the reference's own algorithm (state enumeration on an (e,c) grid) ----
+ * Replaces the whole hot loop of MIDASPOM.out, main_MIDASPOM.c:198-290 (state tables) and :341-395
+ * (compPePc, Pe.Pc, forward recursion): loglik_out[ie*nstep+ic] = log L(e_ie, c_ic) on the grid
+ * ecmin + i*(ecmax-ecmin)/(nstep-1); ltot_out (nullable) = the "Total log-likelihood" of :414-425;
+ * state_info (nullable, 4 ints) = variable patches, enumerated states, short-list states, max states/year.
+ * Linear habitat only (flags -m -> a = 1/m, -d, -p, -s, -l, -u).  At most 24 variable patches. */
+int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches, double a, double d, double prior_occ,
+                       int nstep, double ecmin, double ecmax, double *loglik_out, double *ltot_out, int *state_info);
+const char *mp_exact_last_error(void);
 
 /* ---- plumbing ---- */
 int mp_device_ptr(mp_engine *h, int which, void **ptr, size_t *bytes);

@@ -654,13 +654,13 @@ int mp_get_draws(mp_engine *h, int first, int count, double *out)
 }
 
 // ---- forward simulator
-extern "C++" template <typename R> int simulate_t(mp_engine *h, const mp_params &p, const uint8_t *d_z0, int nyears, int nsims,
-                                            uint64_t seed, int era_all, uint8_t *d_zout, int32_t *d_occ, uint8_t *d_work)
+extern "C++" template <typename R> int simulate_t(mp_engine *h, const mp_params *d_pars, int per_sim, const uint8_t *d_z0, int nyears,
+                                                  int nsims, uint64_t seed, int era_all, uint8_t *d_zout, int32_t *d_occ, uint8_t *d_work)
 {
     Timed tm(h, MP_K_SIM);
     const double *area = h->have_area ? h->d_area : nullptr;
     const int nthr = (int)std::min<size_t>(256, ((nN(h) + 31) / 32) * 32);
-#define SIM(G) k_simulate<R, G><<<nsims, nthr, 0, h->stream>>>(view<R>(h), p, area, d_z0, nyears, seed, 0u, era_all, d_zout, d_occ, d_work)
+#define SIM(G) k_simulate<R, G><<<nsims, nthr, 0, h->stream>>>(view<R>(h), d_pars, per_sim, area, d_z0, nyears, seed, 0u, era_all, d_zout, d_occ, d_work)
     switch (h->geom) {
     case MP_GEOM_LINEAR: SIM(MP_GEOM_LINEAR); break;
     case MP_GEOM_COORDS: SIM(MP_GEOM_COORDS); break;
@@ -670,34 +670,49 @@ extern "C++" template <typename R> int simulate_t(mp_engine *h, const mp_params 
     CK(cudaGetLastError());
     return MP_OK;
 }
-int mp_simulate(mp_engine *h, const mp_params *par, const uint8_t *z0, int nyears, int nsims, uint64_t seed, int era_all,
-                uint8_t *z_out, int32_t *occupied_out)
+static int simulate_impl(mp_engine *h, const mp_params *par, int per_sim, const uint8_t *z0, int nyears, int nsims, uint64_t seed,
+                         int era_all, uint8_t *z_out, int32_t *occupied_out)
 {
     if (!h || !par || !z0) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
     REQUIRE(h->have_landscape, MP_ERR_STATE, "landscape not set");
-    REQUIRE(nyears >= 1 && nsims >= 1 && par->K > 0.0, MP_ERR_ARG, "mp_simulate: need nyears>=1, nsims>=1, K>0");
-    const size_t N = nN(h);
+    REQUIRE(nyears >= 1 && nsims >= 1, MP_ERR_ARG, "mp_simulate: need nyears>=1, nsims>=1");
+    const int npar = per_sim ? nsims : 1;
+    for (int i = 0; i < npar; i++) REQUIRE(par[i].K > 0.0 && par[i].alpha > 0.0, MP_ERR_ARG, "mp_simulate: need K>0 and alpha>0");
+    const size_t N = nN(h), nz0 = per_sim ? (size_t)nsims * N : N;
     uint8_t *d_z0 = nullptr, *d_zout = nullptr, *d_work = nullptr;
     int32_t *d_occ = nullptr;
+    mp_params *d_pars = nullptr;
     int rc = MP_OK;
     cudaError_t e;
 #define SIMCK(call) if ((e = (call)) != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e); rc = MP_ERR_CUDA; goto done; }
-    SIMCK(cudaMalloc(&d_z0, N));
+    SIMCK(cudaMalloc(&d_z0, nz0));
+    SIMCK(cudaMalloc(&d_pars, (size_t)npar * sizeof(mp_params)));
     SIMCK(cudaMalloc(&d_work, (size_t)nsims * 2 * N));
     if (z_out) SIMCK(cudaMalloc(&d_zout, (size_t)nsims * (nyears + 1) * N));
     if (occupied_out) SIMCK(cudaMalloc(&d_occ, (size_t)nsims * (nyears + 1) * 4));
-    SIMCK(cudaMemcpyAsync(d_z0, z0, N, cudaMemcpyHostToDevice, h->stream));
-    rc = is64(h) ? simulate_t<double>(h, *par, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work)
-                 : simulate_t<float>(h, *par, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work);
+    SIMCK(cudaMemcpyAsync(d_z0, z0, nz0, cudaMemcpyHostToDevice, h->stream));
+    SIMCK(cudaMemcpyAsync(d_pars, par, (size_t)npar * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
+    rc = is64(h) ? simulate_t<double>(h, d_pars, per_sim, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work)
+                 : simulate_t<float>(h, d_pars, per_sim, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work);
     if (rc != MP_OK) goto done;
     if (z_out) SIMCK(cudaMemcpyAsync(z_out, d_zout, (size_t)nsims * (nyears + 1) * N, cudaMemcpyDeviceToHost, h->stream));
     if (occupied_out) SIMCK(cudaMemcpyAsync(occupied_out, d_occ, (size_t)nsims * (nyears + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
     SIMCK(cudaStreamSynchronize(h->stream));
 #undef SIMCK
 done:
-    cudaFree(d_z0); cudaFree(d_work); cudaFree(d_zout); cudaFree(d_occ);
+    cudaFree(d_z0); cudaFree(d_pars); cudaFree(d_work); cudaFree(d_zout); cudaFree(d_occ);
     return rc;
+}
+int mp_simulate(mp_engine *h, const mp_params *par, const uint8_t *z0, int nyears, int nsims, uint64_t seed, int era_all,
+                uint8_t *z_out, int32_t *occupied_out)
+{
+    return simulate_impl(h, par, 0, z0, nyears, nsims, seed, era_all, z_out, occupied_out);
+}
+int mp_simulate_ensemble(mp_engine *h, const mp_params *par_per_sim, const uint8_t *z0_per_sim, int nyears, int nsims,
+                         uint64_t seed, int era_all, uint8_t *z_out, int32_t *occupied_out)
+{
+    return simulate_impl(h, par_per_sim, 1, z0_per_sim, nyears, nsims, seed, era_all, z_out, occupied_out);
 }
 
 // ---- plumbing

@@ -1,0 +1,292 @@
+// mp_exact.cu -- the reference's OWN algorithm (exact likelihood by state enumeration on a
+// parameter grid) on the GPU, FP64.  Rows a5-a7 of SURVEY section 8 and "next" row f3.
+//
+// Reference (paths under /root/reference/sources/):
+//   state tables   main_MIDASPOM.c:198-290   piall, npstates, pstates, simppstates, priorst, all2short
+//                                            (bit order: MSB = first variable patch, :206-207,244,247)
+//   S and pC       main_MIDASPOM.c:350-358   (independent of (e, c): computed ONCE here, the reference
+//                                            recomputes it for each of the 10,201 grid points)
+//   compPePc       main_MIDASPOM.c:18-50     Pe[i][j] = E^s1 (1-E)^s2, Pc[j][i] = prod_k (...)
+//   Pe.Pc          main_MIDASPOM.c:363       cblas_dgemm, nextid x nstates x nextid
+//   forward pass   main_MIDASPOM.c:368-392   product over years of the gathered sub-blocks of P
+//   dieoff / loss  main_MIDASPOM_dieoff.c:307-351, main_MIDASPOM_loss.c:345-386
+//
+// Layout: the integer tables are built on the host exactly as the reference builds them (they are
+// tiny); one CTA per grid point evaluates P = Pe.Pc with the enumerated states streamed in chunks
+// through shared memory, then one thread runs the forward recursion.  All sums in FP64, states in
+// ascending order (the order of the reference's dgemm), so results agree to ~1e-15 relative.
+//
+// One deliberate difference: with -1 cells in the FIRST row the reference multiplies by a partly
+// uninitialised Pold (main_MIDASPOM.c:368-369,379).  Here Pold starts as the
+// identity -- the evident intent, and what the data-augmented likelihood sums to.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include "../../include/libmidaspom_cuda.h"
+
+namespace {
+
+thread_local std::string g_exact_error;
+
+#define XCK(call)                                                                       \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                              \
+        g_exact_error = std::string(#call) + ": " + cudaGetErrorString(e_); rc = MP_ERR_CUDA; goto done; } } while (0)
+
+struct Tables {
+    int n = 0, T = 0, nvar = 0, nextid = 0;
+    uint32_t nstates = 0;
+    std::vector<int> var;                 // n
+    std::vector<uint32_t> zmask_all;      // nstates: bit k (patch k) of enumerated state
+    std::vector<int> npstates;            // T
+    std::vector<std::vector<uint32_t>> pstates, simpp;   // per year
+    std::vector<float> priorst;           // npstates[0]   (float like the reference, :218)
+    std::vector<uint32_t> all2short;      // nextid -> enumerated state id
+};
+
+// patch-bit mask (bit k = patch k occupied) of enumerated state id: piall[i][j] = i / 2^(nvar-jt-1) % 2  (:203-209)
+static uint32_t state_mask(const Tables &tb, uint32_t id)
+{
+    uint32_t m = 0; int jt = 0;
+    for (int j = 0; j < tb.n; j++)
+        if (tb.var[j]) { if ((id >> (tb.nvar - jt - 1)) & 1u) m |= 1u << j; jt++; }
+    return m;
+}
+
+static int build_tables(const int8_t *obs, int T, int n, float prioroc, Tables &tb)
+{
+    tb.n = n; tb.T = T;
+    tb.var.assign(n, 0);
+    for (int i = 0; i < T; i++) for (int j = 0; j < n; j++) if (obs[(size_t)i * n + j] != 0) tb.var[j] = 1;   // :162-164
+    tb.nvar = 0; for (int j = 0; j < n; j++) tb.nvar += tb.var[j];
+    if (tb.nvar > 24 || n > 31) { g_exact_error = "exact engine: more than 24 variable patches (2^nvar states)"; return MP_ERR_UNSUPPORTED; }
+    tb.nstates = 1u << tb.nvar;
+    tb.zmask_all.resize(tb.nstates);
+    for (uint32_t i = 0; i < tb.nstates; i++) tb.zmask_all[i] = state_mask(tb, i);
+    tb.npstates.assign(T, 0); tb.pstates.assign(T, {}); tb.simpp.assign(T, {});
+    tb.nextid = 0;
+    for (int i = 0; i < T; i++) {                                                  // :222-279
+        int s1 = 0;
+        for (int j = 0; j < n; j++) if (obs[(size_t)i * n + j] == -1) s1++;
+        if (s1 > 20) { g_exact_error = "exact engine: more than 20 missing cells in one year"; return MP_ERR_UNSUPPORTED; }
+        const uint32_t np = 1u << s1;
+        tb.npstates[i] = (int)np;
+        if (i == 0) tb.priorst.assign(np, 1.0f);
+        tb.pstates[i].assign(np, 0); tb.simpp[i].assign(np, 0);
+        s1 = 0; int jt = 0;
+        for (int j = 0; j < n; j++) {
+            const int o = obs[(size_t)i * n + j];
+            if (o == -1) s1++;
+            for (uint32_t k = 0; k < np; k++) {
+                if (o > -1) { if (o == 1) tb.pstates[i][k] += 1u << (tb.nvar - jt - 1); }      // :244 (o == 1 implies var[j])
+                else {
+                    const uint32_t st1 = np >> s1;                                  // npstates / 2^s1
+                    const uint32_t bit = (k / st1) % 2;
+                    tb.pstates[i][k] += bit << (tb.nvar - jt - 1);
+                    if (i == 0) tb.priorst[k] *= (float)bit * prioroc + (float)(1 - bit) * (1 - prioroc);   // :249, float arithmetic
+                }
+            }
+            if (tb.var[j]) jt++;
+        }
+        for (uint32_t k = 0; k < np; k++) {                                        // :256-278
+            if (i == 0) { tb.simpp[0][k] = tb.nextid++; continue; }
+            bool present = false;
+            for (int j = 0; j < i; j++)
+                for (uint32_t l = 0; l < (uint32_t)tb.npstates[j]; l++)
+                    if (tb.pstates[i][k] == tb.pstates[j][l]) { tb.simpp[i][k] = tb.simpp[j][l]; present = true; }
+            if (!present) tb.simpp[i][k] = tb.nextid++;
+        }
+    }
+    tb.all2short.assign(tb.nextid, 0);
+    for (int i = 0; i < T; i++) for (uint32_t k = 0; k < (uint32_t)tb.npstates[i]; k++) tb.all2short[tb.simpp[i][k]] = tb.pstates[i][k];   // :282-287
+    return MP_OK;
+}
+
+// S[j][k] = sum_{l != k} M[l][k] y_l(j), M[l][k] = exp(-a |l-k| d)   (:180-188, :351-355); l ascending
+__global__ void k_exact_S(const uint32_t *__restrict__ masks, uint32_t nstates, int n, double a, double d, double *__restrict__ S)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nstates) return;
+    const uint32_t m = masks[j];
+    for (int k = 0; k < n; k++) {
+        double s = 0.0;
+        for (int l = 0; l < n; l++)
+            if (l != k && ((m >> l) & 1u)) s += exp(-a * (double)(l > k ? l - k : k - l) * d);
+        S[(size_t)j * n + k] = s;
+    }
+}
+
+constexpr int XCHUNK = 64;      // enumerated states per shared-memory chunk
+constexpr int XMAXID = 32;      // nextid <= 32 handled by the fused kernel (P held per thread pair)
+
+// One CTA per grid point: P[i][i'] = sum_j Pe[i][j] Pc[j][i'] over all enumerated states j (ascending),
+// then the forward recursion of main_MIDASPOM.c:368-392 and Lik = log sum.
+__global__ void __launch_bounds__(256)
+k_exact_grid(const uint32_t *__restrict__ masks, uint32_t nstates, int n, const double *__restrict__ S,
+             const uint32_t *__restrict__ short_masks, int nextid, const double *__restrict__ egrid,
+             const double *__restrict__ cgrid, int nstep, int T, const int *__restrict__ npstates,
+             const int *__restrict__ simpp_off, const uint32_t *__restrict__ simpp, const float *__restrict__ priorst,
+             double *__restrict__ Pout, double *__restrict__ lik, double *__restrict__ work)
+{
+    __shared__ double sPe[XCHUNK][XMAXID], sPc[XCHUNK][XMAXID];
+    const int gp = blockIdx.x, ie = gp / nstep, ic = gp - ie * nstep;
+    double E = egrid[ie]; if (E > 1.0) E = 1.0;                                     // compPePc:21-22
+    const double c = cgrid[ic];
+    const int tid = threadIdx.x;
+    // each thread owns the entries tid, tid+256, ... of P (nextid^2 <= 1024)
+    constexpr int MAXOWN = (XMAXID * XMAXID + 255) / 256;
+    double acc[MAXOWN];
+#pragma unroll
+    for (int o = 0; o < MAXOWN; o++) acc[o] = 0.0;
+    for (uint32_t j0 = 0; j0 < nstates; j0 += XCHUNK) {
+        // factors of the chunk: thread handles (state, short state) pairs
+        for (int p = tid; p < XCHUNK * nextid; p += 256) {
+            const int js = p / nextid, i = p - js * nextid;
+            const uint32_t j = j0 + js;
+            double pe = 0.0, pc = 0.0;
+            if (j < nstates) {
+                const uint32_t y = masks[j], zs = short_masks[i];
+                if ((y & ~zs) == 0u) {                                              // compPePc:34-37  (0 -> 1 impossible)
+                    const int s1 = __popc(zs & ~y), s2 = __popc(zs & y);            // :38-39
+                    pe = pow(E, (double)s1) * pow(1.0 - E, (double)s2);             // :43
+                    pc = 1.0;
+                    for (int k = 0; k < n; k++) {                                   // :40
+                        if ((y >> k) & 1u) continue;
+                        double pC = c * S[(size_t)j * n + k];                       // :356-357
+                        if (pC > 1.0) pC = 1.0;
+                        pc *= ((zs >> k) & 1u) ? pC : 1.0 - pC;
+                    }
+                }
+            }
+            sPe[js][i] = pe; sPc[js][i] = pc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < MAXOWN; o++) {
+            const int ent = tid + o * 256;
+            if (ent < nextid * nextid) {
+                const int a = ent / nextid, b = ent - a * nextid;
+                double s = acc[o];
+                for (int js = 0; js < XCHUNK; js++) s += sPe[js][a] * sPc[js][b];
+                acc[o] = s;
+            }
+        }
+        __syncthreads();
+    }
+    double *P = Pout + (size_t)gp * nextid * nextid;
+#pragma unroll
+    for (int o = 0; o < MAXOWN; o++) { const int ent = tid + o * 256; if (ent < nextid * nextid) P[ent] = acc[o]; }
+    __syncthreads();
+    if (tid != 0) return;
+    // forward recursion (:368-392); Pold (np0 x np_{t-1}) starts as the identity
+    int maxnp = 1;
+    for (int t = 0; t < T; t++) if (npstates[t] > maxnp) maxnp = npstates[t];
+    const int np0 = npstates[0];
+    double *A = work + (size_t)gp * 2 * np0 * maxnp, *B = A + (size_t)np0 * maxnp;
+    for (int k = 0; k < np0; k++) for (int l = 0; l < np0; l++) A[k * np0 + l] = k == l ? 1.0 : 0.0;
+    for (int t = 1; t < T; t++) {
+        const int npp = npstates[t - 1], npc = npstates[t];
+        const uint32_t *sp = simpp + simpp_off[t - 1], *sc = simpp + simpp_off[t];
+        for (int k = 0; k < np0; k++)
+            for (int l = 0; l < npc; l++) {
+                double s = 0.0;
+                for (int m = 0; m < npp; m++) s += A[k * npp + m] * P[sp[m] * nextid + sc[l]];   // :375,379
+                B[k * npc + l] = s;
+            }
+        double *tmp = A; A = B; B = tmp;
+    }
+    double L = 0.0;
+    const int npl = npstates[T - 1];
+    for (int k = 0; k < np0; k++) for (int l = 0; l < npl; l++) L += A[k * npl + l] * (double)priorst[k];   // :386-390
+    lik[gp] = log(L);                                                               // :392
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mp_exact_last_error(void) { return g_exact_error.c_str(); }
+
+// Exact log-likelihood of the observations on an nstep x nstep grid of (e, c) -- the table
+// MIDASPOM.out computes (main_MIDASPOM.c:341-395).  loglik_out[ie*nstep+ic] = log L(e_ie, c_ic);
+// ltot_out (nullable) = 2 log(win) + log sum coef exp(Lik) (:414-424).  state_info (nullable, 4 ints):
+// n variable patches, enumerated states, short-list states, max states per year.
+int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches, double a, double d, double prior_occ,
+                       int nstep, double ecmin, double ecmax, double *loglik_out, double *ltot_out, int *state_info)
+{
+    if (!obs || !loglik_out || n_years < 2 || n_patches < 1 || nstep < 2) { g_exact_error = "mp_exact_posterior: bad argument"; return MP_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_exact_error = "mp_exact_posterior: no CUDA device; there is no CPU fallback"; return MP_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { g_exact_error = "mp_exact_posterior: bad device ordinal"; return MP_ERR_ARG; }
+    Tables tb;
+    int rc = build_tables(obs, n_years, n_patches, (float)prior_occ, tb);
+    if (rc != MP_OK) return rc;
+    if (tb.nextid > XMAXID) { g_exact_error = "exact engine: more than 32 distinct observation-compatible states"; return MP_ERR_UNSUPPORTED; }
+    const int n = n_patches, T = n_years, ng = nstep * nstep;
+    // grid axes (:312-319): i*win + ecmin, last = ecmax
+    const double win = (ecmax - ecmin) / (nstep - 1);
+    std::vector<double> axis(nstep);
+    for (int i = 0; i < nstep - 1; i++) axis[i] = (double)i * win + ecmin;
+    axis[nstep - 1] = ecmax;
+    std::vector<uint32_t> short_masks(tb.nextid);
+    for (int i = 0; i < tb.nextid; i++) short_masks[i] = tb.zmask_all[tb.all2short[i]];
+    std::vector<int> simpp_off(T + 1, 0);
+    std::vector<uint32_t> simpp_flat;
+    int maxnp = 1;
+    for (int t = 0; t < T; t++) {
+        simpp_off[t] = (int)simpp_flat.size();
+        simpp_flat.insert(simpp_flat.end(), tb.simpp[t].begin(), tb.simpp[t].end());
+        if (tb.npstates[t] > maxnp) maxnp = tb.npstates[t];
+    }
+    if (state_info) { state_info[0] = tb.nvar; state_info[1] = (int)tb.nstates; state_info[2] = tb.nextid; state_info[3] = maxnp; }
+
+    uint32_t *d_masks = nullptr, *d_short = nullptr, *d_simpp = nullptr;
+    double *d_S = nullptr, *d_axis = nullptr, *d_P = nullptr, *d_lik = nullptr, *d_work = nullptr;
+    int *d_np = nullptr, *d_off = nullptr;
+    float *d_prior = nullptr;
+    XCK(cudaSetDevice(device));
+    XCK(cudaMalloc(&d_masks, (size_t)tb.nstates * 4));
+    XCK(cudaMalloc(&d_short, (size_t)tb.nextid * 4));
+    XCK(cudaMalloc(&d_simpp, simpp_flat.size() * 4));
+    XCK(cudaMalloc(&d_S, (size_t)tb.nstates * n * 8));
+    XCK(cudaMalloc(&d_axis, (size_t)nstep * 8));
+    XCK(cudaMalloc(&d_P, (size_t)ng * tb.nextid * tb.nextid * 8));
+    XCK(cudaMalloc(&d_lik, (size_t)ng * 8));
+    XCK(cudaMalloc(&d_work, (size_t)ng * 2 * tb.npstates[0] * maxnp * 8));
+    XCK(cudaMalloc(&d_np, (size_t)T * 4));
+    XCK(cudaMalloc(&d_off, (size_t)(T + 1) * 4));
+    XCK(cudaMalloc(&d_prior, tb.priorst.size() * 4));
+    XCK(cudaMemcpy(d_masks, tb.zmask_all.data(), (size_t)tb.nstates * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_short, short_masks.data(), (size_t)tb.nextid * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_simpp, simpp_flat.data(), simpp_flat.size() * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_axis, axis.data(), (size_t)nstep * 8, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_np, tb.npstates.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_off, simpp_off.data(), (size_t)(T + 1) * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_prior, tb.priorst.data(), tb.priorst.size() * 4, cudaMemcpyHostToDevice));
+    k_exact_S<<<(tb.nstates + 127) / 128, 128>>>(d_masks, tb.nstates, n, a, d, d_S);
+    XCK(cudaGetLastError());
+    k_exact_grid<<<ng, 256>>>(d_masks, tb.nstates, n, d_S, d_short, tb.nextid, d_axis, d_axis, nstep, T, d_np, d_off, d_simpp,
+                              d_prior, d_P, d_lik, d_work);
+    XCK(cudaGetLastError());
+    XCK(cudaMemcpy(loglik_out, d_lik, (size_t)ng * 8, cudaMemcpyDeviceToHost));
+    if (ltot_out) {                                                                 // :414-424 (host, nstep^2 terms)
+        double Ltot = 0.0;
+        for (int k = 0; k < nstep; k++)
+            for (int l = 0; l < nstep; l++) {
+                double coef = 1.0;
+                if (k == 0 || k == nstep - 1) coef *= 0.5;
+                if (l == 0 || l == nstep - 1) coef *= 0.5;
+                Ltot += exp(loglik_out[(size_t)k * nstep + l]) * coef;
+            }
+        *ltot_out = 2.0 * log(win) + log(Ltot);
+    }
+done:
+    cudaFree(d_masks); cudaFree(d_short); cudaFree(d_simpp); cudaFree(d_S); cudaFree(d_axis); cudaFree(d_P);
+    cudaFree(d_lik); cudaFree(d_work); cudaFree(d_np); cudaFree(d_off); cudaFree(d_prior);
+    return rc;
+}
+
+}  // extern "C"

@@ -574,13 +574,15 @@ k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__res
 // One CTA per simulated trajectory (future.c:359-386 loops over simulations; simpij :64-110 is one
 // year).  survive iff u > E (:78); colonise iff u < C (:100).
 template <typename R, int GEOM>
-__global__ void k_simulate(Landscape<R> ls, mp_params p, const double *__restrict__ area, const uint8_t *__restrict__ z0,
-                           int nyears, uint64_t seed, uint32_t sim0, int era_all, uint8_t *__restrict__ z_out,
-                           int32_t *__restrict__ occ_out, uint8_t *__restrict__ work)
+__global__ void k_simulate(Landscape<R> ls, const mp_params *__restrict__ pars, int per_sim, const double *__restrict__ area,
+                           const uint8_t *__restrict__ z0_all, int nyears, uint64_t seed, uint32_t sim0, int era_all,
+                           uint8_t *__restrict__ z_out, int32_t *__restrict__ occ_out, uint8_t *__restrict__ work)
 {
     __shared__ double scratch[32];
     const int n = ls.n, tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t sim = sim0 + blockIdx.x;
+    const mp_params p = pars[per_sim ? blockIdx.x : 0];                  // per-trajectory parameters and start (future.c:359-381)
+    const uint8_t *z0 = z0_all + (per_sim ? (size_t)blockIdx.x * n : 0);
     uint8_t *zc = work + (size_t)blockIdx.x * 2 * n, *yc = zc + n;     // current state, intermediate state
     const Trans<R> tr = make_trans<R>(p, era_all);
     int cnt = 0;

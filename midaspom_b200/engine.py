@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "mp_set_scales", "mp_get_scales", "mp_connectivity", "mp_get_connectivity", "mp_loglik", "mp_loglik_host",
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
-    "mp_get_timing", "mp_probe_peaks", "mp_get_stream",
+    "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble",
 )
 
 
@@ -106,11 +106,15 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_num_draws.argtypes = [vp]; L.mp_reset_draws.argtypes = [vp]; L.mp_sweep_index.argtypes = [vp]
     L.mp_get_draws.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mp_simulate.argtypes = [vp, pp, u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, u8p, C.POINTER(C.c_int32)]
+    L.mp_simulate_ensemble.argtypes = [vp, pp, u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, u8p, C.POINTER(C.c_int32)]
     L.mp_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mp_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.mp_set_timing.argtypes = [vp, C.c_int]
     L.mp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
     L.mp_probe_peaks.argtypes = [vp, dp]
+    L.mp_exact_posterior.argtypes = [C.c_int, i8p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                     C.c_double, C.c_double, dp, dp, C.POINTER(C.c_int)]
+    L.mp_exact_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -311,6 +315,19 @@ class Engine:
                                       _p(z_out, _u8p), _p(occ, C.POINTER(C.c_int32))), "mp_simulate")
         return z_out, occ
 
+    def simulate_ensemble(self, params, z0, nyears, seed=1, era_all=False, want_states=False):
+        """One parameter set and one start state per trajectory (mp_simulate_ensemble)."""
+        z0 = np.ascontiguousarray(z0, dtype=np.uint8)
+        nsims = z0.shape[0]
+        arr = (MpParams * nsims)()
+        for i, p in enumerate(params):
+            arr[i] = self._one_param(p)
+        z_out = np.zeros((nsims, nyears + 1, self.N), dtype=np.uint8) if want_states else None
+        occ = np.zeros((nsims, nyears + 1), dtype=np.int32)
+        self._ck(self.lib.mp_simulate_ensemble(self.h, arr, _p(z0, _u8p), nyears, nsims, seed, int(era_all), _p(z_out, _u8p),
+                                               _p(occ, C.POINTER(C.c_int32))), "mp_simulate_ensemble")
+        return z_out, occ
+
     @staticmethod
     def _one_param(p):
         d = dict(PARAM_DEFAULTS)
@@ -342,3 +359,19 @@ class Engine:
         out = np.zeros(4)
         self._ck(self.lib.mp_probe_peaks(self.h, _p(out, _dp)), "mp_probe_peaks")
         return dict(mufu_gops=out[0], ffma_gfma=out[1], dadd_gops=out[2], copy_gbs=out[3])
+
+
+def exact_posterior(obs, a=1.0 / 400.0, d=100.0, prior_occ=0.5, nstep=101, ecmin=0.0, ecmax=1.0, device=0):
+    """mp_exact_posterior: the reference's exact grid likelihood (MIDASPOM.out's table) on the GPU.
+    Returns (loglik[nstep, nstep], ltot, info dict); posterior density = exp(loglik - ltot)."""
+    lib = load_library()
+    obs = np.ascontiguousarray(obs, dtype=np.int8)
+    T, n = obs.shape
+    ll = np.zeros((nstep, nstep))
+    ltot = C.c_double()
+    info = (C.c_int * 4)()
+    rc = lib.mp_exact_posterior(device, _p(obs, _i8p), T, n, float(a), float(d), float(prior_occ), int(nstep), float(ecmin),
+                                float(ecmax), _p(ll, _dp), C.byref(ltot), info)
+    if rc != 0:
+        raise MpError(f"mp_exact_posterior failed ({rc}): {lib.mp_exact_last_error().decode()}")
+    return ll, ltot.value, dict(nvar=info[0], nstates=info[1], nextid=info[2], max_states_per_year=info[3])

@@ -18,6 +18,7 @@ What is recorded (all produced by reference code, none by our oracle):
   cpp_*              compPePc (serial product form and MPI log form) on the example's state tables
   var_*              pije / pijc / pijcsource / dieoff variants on random 6-patch state triples
   simpij_*           10,000 draws of simpij from one state (libc rand(), srand(12345))
+  future_*_runs      6 runs of `MIDASPOM_future.out -a 50 -m 400 -d 100 -q posterior.txt` (run_examples.sh:17,20): extinct counts per year
 """
 import ctypes as C
 import re
@@ -166,6 +167,17 @@ def main():
         R.ref_future_simpij(z0.ctypes.data_as(ip), new.ctypes.data_as(ip), e_, c_, K_, Ks_, Mf.ctypes.data_as(dp), n8)
         acc += new
     g["simpij_z0"], g["simpij_pars"], g["simpij_freq"], g["simpij_nsim"] = z0, np.array([e_, c_, K_, Ks_, 1.0 / 400, 100.0, 500.0]), acc / nsim, np.array(nsim)
+
+    # ---- future module: the program itself, 6 runs of 10,000 simulations each (rand() is time-seeded)
+    import shutil, time
+    shutil.copy(EXAMPLE, HERE / "occupancies_example.txt")          # the bundled 7-line input (data, read by the driver tests)
+    for tag, extra in (("nomgmt", []), ("source", ["-S", "1", "-s", "500"])):
+        runs = []
+        for r in range(6):
+            run("MIDASPOM_future.out", ["-a", "50", "-m", "400", "-d", "100", "-i", EXAMPLE, "-q", str(tmp / "p.txt"), "-o", str(tmp / "f.txt")] + extra)
+            runs.append([int(v) for v in (tmp / "f.txt").read_text().split()])
+            time.sleep(1.1)                                          # srand(time(NULL)) has one-second resolution
+        g[f"future_{tag}_runs"] = np.array(runs)
 
     np.savez_compressed(HERE / "golden.npz", **g)
     print("wrote", HERE / "golden.npz", {k: np.shape(v) for k, v in g.items()})

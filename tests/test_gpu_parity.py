@@ -156,6 +156,41 @@ def test_loglik_bundled_example_complete_data_terms(golden, example_obs):
     rel_close(ll, want, 1e-12, floor=1.0)
 
 
+# ------------------------------------------------------------------ exact small-n engine (a5-a7): the reference's own output
+def test_exact_engine_reproduces_reference_posterior_tables(golden, example_obs):
+    """mp_exact_posterior == MIDASPOM.out on the bundled example: the 101x101 table of
+    run_examples.sh:8, the -s 11 table with its zero-likelihood edges, the -s 3 -l .3 -u .7 grid,
+    the 'Total log-likelihood' line, and the state bookkeeping the program prints."""
+    for key, nstep, lo, hi in (("post_default", 101, 0.0, 1.0), ("post_s11", 11, 0.0, 1.0), ("post_s3", 3, 0.3, 0.7)):
+        ll, ltot, info = mb.exact_posterior(example_obs, a=A, d=100.0, prior_occ=0.5, nstep=nstep, ecmin=lo, ecmax=hi)
+        tab = golden[key]
+        assert info == dict(nvar=8, nstates=256, nextid=10, max_states_per_year=2)       # main_MIDASPOM.c:300-304 echo
+        assert abs(ltot - float(golden["ltot_" + key.split("_")[1]])) < 6e-6             # printed with %.5lf
+        dens = np.exp(ll - ltot)
+        assert (dens[tab == 0] < 5.1e-21).all()                                          # printed as 0.00000000000000000000
+        np.testing.assert_allclose(dens, tab, rtol=1e-9, atol=5.1e-21)                   # table printed with %.20lf
+    ll3, _, _ = mb.exact_posterior(example_obs, a=A, d=100.0, nstep=3, ecmin=0.3, ecmax=0.7)
+    np.testing.assert_allclose(ll3, golden["loglik_s3_survey"], rtol=0, atol=2e-12)
+
+
+def test_exact_engine_matches_oracle_marginal_on_random_small_landscapes():
+    """Random 6-10 patch histories with missing cells (also in year 0, where the reference itself
+    reads uninitialised memory): exact engine == oracle's forward recursion."""
+    rng = np.random.default_rng(77)
+    for n, T, miss0 in ((6, 5, False), (9, 4, True), (10, 6, True), (7, 3, False)):
+        z = (rng.random((T, n)) < 0.55).astype(np.int8)
+        z[:, rng.integers(n)] = 0                                  # a never-occupied patch: dropped from the enumeration (:203-204)
+        obs = z.copy()
+        obs[1:][rng.random((T - 1, n)) < 0.12] = -1
+        if miss0:
+            obs[0, rng.choice(n, 2, replace=False)] = -1
+        m = O.Model(obs, spacing=150.0, prior_occ=0.25)
+        ll, ltot, info = mb.exact_posterior(obs, a=1 / 300, d=150.0, prior_occ=0.25, nstep=5, ecmin=0.1, ecmax=0.9)
+        grid = [0.1, 0.3, 0.5, 0.7, 0.9]
+        want = np.array([[O.marginal_loglik(m, O.params(e=e, c=c, alpha=1 / 300)) for c in grid] for e in grid])
+        rel_close(ll, want, 1e-10, floor=1.0)
+
+
 # ------------------------------------------------------------------ rank-1 flips
 @pytest.mark.parametrize("precision", [mb.FP64, mb.FP32])
 @pytest.mark.parametrize("geom", [O.GEOM_LINEAR, O.GEOM_COORDS, O.GEOM_DENSE])
