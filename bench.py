@@ -299,12 +299,68 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- cfg1: the bundled example, exact grid posterior
+def run_cfg1(args, rank):
+    """BASELINE config[0]: `MIDASPOM.out -m 400 -d 100` on the bundled 8 x 7 example = 101 x 101 = 10,201 exact
+    likelihood evaluations (run_examples.sh:8).  ours: mp_exact_posterior (host buffers in and out);
+    reference: the reference binary itself, compiled from its sources into oracle/_ref (kind "reference")."""
+    if rank != 0:
+        return
+    import tempfile
+    example = ROOT / "tests" / "golden" / "occupancies_example.txt"
+    nev = 101 * 101
+    cfgd = dict(workload="cfg1: bundled example (8 patches x 7 years), 101 x 101 grid of (e, c), exact likelihood", grid=101)
+    if args.impl == "reference":
+        exe = ROOT / "oracle" / "_ref" / "MIDASPOM.out"
+        if not exe.exists():
+            print(json.dumps(dict(impl="reference", unavailable="oracle/_ref/MIDASPOM.out not built (no /root/reference at build time)")))
+            return
+        tmp = tempfile.mkdtemp()
+        times = []
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            subprocess.run([str(exe), "-m", "400", "-d", "100", "-i", str(example), "-o", f"{tmp}/p.txt"], check=True, capture_output=True)
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        t = float(np.mean(times))
+        v = nev / t
+        print(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=args.gpus, steps=args.steps,
+                              warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                              data="bundled example", impl="reference", config=cfgd,
+                              cpu_baseline=dict(value=v, unit="likelihood evaluations/s", cores=1, kind="reference",
+                                                sample="MIDASPOM.out (reference sources, gcc -O3, naive cblas_dgemm), whole program incl. file I/O, single thread"),
+                              e2e=dict(value=v, unit="likelihood evaluations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+    import torch
+    import midaspom_b200 as mb
+    raw = example.read_bytes()
+    n = 1 + sum(1 for ch in raw.split(b"\n", 1)[0] if ch in b" \t")
+    tmax = raw.count(b"\n")
+    obs = np.array([int(v) for v in raw.split()][: n * tmax], dtype=np.int8).reshape(tmax, n)
+    times = []
+    for s in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ll, ltot, info = mb.exact_posterior(obs, a=1 / 400, d=100.0, prior_occ=0.5, nstep=101)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    v = nev / t
+    print(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                          ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="bundled example",
+                          config=dict(cfgd, states=info["nstates"], short_states=info["nextid"], total_loglik=ltot),
+                          e2e=dict(value=v, unit="likelihood evaluations/s", h2d_bytes_per_step=int(obs.nbytes), d2h_bytes_per_step=nev * 8),
+                          gpu_launches=2 * args.steps)))
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.impl == "reference":
+    if args.workload == "cfg1":
+        run_cfg1(args, rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)

@@ -116,7 +116,7 @@ static int pick_cluster(int tasks, int sms, int max_cs)
 }
 static bool fast_sweep_ok(const mp_engine *h)
 {
-    return !is64(h) && !(h->have_era && h->any_src) && h->cfg.n_patches <= 31 * 1024;
+    return !is64(h) && h->cfg.n_patches <= 31 * 1024;
 }
 static int launch_sweep_y_fast(mp_engine *h)
 {

@@ -204,6 +204,62 @@ k_exact_grid(const uint32_t *__restrict__ masks, uint32_t nstates, int n, const 
     lik[gp] = log(L);                                                               // :392
 }
 
+
+// ---- dieoff / loss: likelihood of the FIRST survey after ts pre-event and tdis post-event unobserved years
+// (dieoff.c:307-351, loss.c:345-386).  The reference forms P = Pe.Pc, matrix powers PK^ts and P^tdis
+// and sums every row of their product; summing the rows first turns that into ts + tdis
+// vector-matrix products  v <- (v.Pe).Pc  starting from v = (1,...,1).  One CTA per grid value.
+__global__ void __launch_bounds__(256)
+k_exact_variant(int n, const double *__restrict__ S, double a, double eB, double cB, const double *__restrict__ Kgrid,
+                const double *__restrict__ dgrid, int nd, int variant, int ts, int tdis, const uint32_t *__restrict__ pst,
+                const float *__restrict__ prior, int npst, double *__restrict__ lik)
+{
+    extern __shared__ double xs[];
+    const uint32_t nstates = 1u << n;
+    double *v = xs, *w = xs + nstates, *powE = w + nstates, *pow1 = powE + 32, *g = pow1 + 32;
+    const int iK = blockIdx.x / nd, id = blockIdx.x - iK * nd, tid = threadIdx.x;
+    const double Kval = Kgrid[iK], dL = dgrid ? dgrid[id] : 0.0;
+    for (uint32_t i = tid; i < nstates; i += 256) v[i] = 1.0;
+    if (tid < n) g[tid] = exp(-a * (double)(tid + 1) * dL);            // loss.c:365  M[n][j] = exp(-a (j+1) d_L)
+    __syncthreads();
+    for (int step = 0; step < ts + tdis; step++) {
+        const bool pre = step < ts;
+        double E = (pre && variant == 1) ? eB / Kval : eB;              // dieoff.c:56-57 ; loss.c:57
+        if (E > 1.0) E = 1.0;
+        const double Kt = (pre && variant == 1) ? Kval : 1.0, Ks = (pre && variant == 2) ? Kval : 0.0;
+        if (tid <= n) { powE[tid] = pow(E, (double)tid); pow1[tid] = pow(1.0 - E, (double)tid); }
+        __syncthreads();
+        for (uint32_t j = tid; j < nstates; j += 256) {                 // w = v . Pe   (pije)
+            double s = 0.0;
+            for (uint32_t i = 0; i < nstates; i++)
+                if ((j & ~i) == 0u) s += v[i] * (powE[__popc(i & ~j)] * pow1[__popc(i & j)]);
+            w[j] = s;
+        }
+        __syncthreads();
+        for (uint32_t t = tid; t < nstates; t += 256) {                 // v = w . Pc   (pijc / pijcsource)
+            double s = 0.0;
+            for (uint32_t j = 0; j < nstates; j++) {
+                if ((j & ~t) != 0u) continue;
+                double pc = 1.0;
+                for (int k = 0; k < n; k++) {
+                    if ((j >> k) & 1u) continue;
+                    double C = variant == 1 ? cB * S[(size_t)j * n + k] * Kt : cB * (S[(size_t)j * n + k] + g[k] * Ks);   // dieoff.c:78 ; loss.c:97-98
+                    if (C > 1.0) C = 1.0;
+                    pc *= ((t >> k) & 1u) ? C : 1.0 - C;
+                }
+                s += w[j] * pc;
+            }
+            v[t] = s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double L = 0.0;
+        for (int j = 0; j < npst; j++) L += v[pst[j]] * (double)prior[j];     // dieoff.c:345-350
+        lik[blockIdx.x] = L;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -286,6 +342,69 @@ int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches
 done:
     cudaFree(d_masks); cudaFree(d_short); cudaFree(d_simpp); cudaFree(d_S); cudaFree(d_axis); cudaFree(d_P);
     cudaFree(d_lik); cudaFree(d_work); cudaFree(d_np); cudaFree(d_off); cudaFree(d_prior);
+    return rc;
+}
+
+
+// dieoff (variant 1: MIDASPOM_dieoff.out) / loss (variant 2: MIDASPOM_loss.out): likelihood of the first
+// survey row on the log-spaced K grid (dieoff.c:283-286) x, for loss, the d_L grid (loss.c:319-322).
+// lik_out: nstepK (dieoff) or nstepK*nstepd (loss) raw likelihoods, as the reference writes them.
+int mp_exact_variant(int device, int variant, const int8_t *first_row, int n_patches, double a, double d, double prior_occ,
+                     double eB, double cB, int ts, int tdis, int nstepK, double Kmin, double Kmax, int nstepd, double dmin,
+                     double dmax, double *lik_out)
+{
+    if (!first_row || !lik_out || n_patches < 1 || n_patches > 14 || nstepK < 2 || ts < 0 || tdis < 0 || (variant != 1 && variant != 2) ||
+        (variant == 2 && nstepd < 2)) { g_exact_error = "mp_exact_variant: bad argument (at most 14 patches)"; return MP_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_exact_error = "mp_exact_variant: no CUDA device; there is no CPU fallback"; return MP_ERR_CUDA; }
+    const int n = n_patches, nd = variant == 2 ? nstepd : 1;
+    const uint32_t nstates = 1u << n;
+    // completions of the -1 cells of the survey row and their prior (dieoff.c:204-233): all 2^n states, bit j of the
+    // id = patch j counted from the MSB (pow(2, n-j-1))
+    int s1 = 0;
+    for (int j = 0; j < n; j++) s1 += first_row[j] == -1;
+    const uint32_t npst = 1u << s1;
+    std::vector<uint32_t> pst(npst, 0);
+    std::vector<float> prior(npst, 1.0f);
+    const float pr = (float)prior_occ;
+    s1 = 0;
+    for (int j = 0; j < n; j++) {
+        if (first_row[j] == -1) s1++;
+        for (uint32_t k = 0; k < npst; k++) {
+            uint32_t bit;
+            if (first_row[j] > -1) bit = first_row[j] == 1;
+            else { const uint32_t st1 = npst >> s1; bit = (k / st1) % 2; prior[k] *= (float)bit * pr + (float)(1 - bit) * (1 - pr); }
+            pst[k] |= bit << j;                                        // our masks use bit j = patch j (see k_exact_S)
+        }
+    }
+    std::vector<uint32_t> masks(nstates);
+    for (uint32_t i = 0; i < nstates; i++) masks[i] = i;               // state id == patch mask (order of the sums is immaterial here)
+    std::vector<double> Kg(nstepK), dg(nd, 0.0);
+    for (int i = 0; i < nstepK; i++) Kg[i] = pow(10.0, ((double)i) / (nstepK - 1) * (log10(Kmax) - log10(Kmin)) + log10(Kmin));
+    if (variant == 2) for (int i = 0; i < nd; i++) dg[i] = i * (dmax - dmin) / (nd - 1) + dmin;
+    int rc = MP_OK;
+    uint32_t *d_masks = nullptr, *d_pst = nullptr;
+    double *d_S = nullptr, *d_K = nullptr, *d_d = nullptr, *d_lik = nullptr;
+    float *d_prior = nullptr;
+    const size_t smem = ((size_t)2 * nstates + 64 + 32) * sizeof(double);
+    XCK(cudaSetDevice(device));
+    XCK(cudaMalloc(&d_masks, (size_t)nstates * 4)); XCK(cudaMalloc(&d_pst, (size_t)npst * 4)); XCK(cudaMalloc(&d_prior, (size_t)npst * 4));
+    XCK(cudaMalloc(&d_S, (size_t)nstates * n * 8)); XCK(cudaMalloc(&d_K, (size_t)nstepK * 8)); XCK(cudaMalloc(&d_d, (size_t)nd * 8));
+    XCK(cudaMalloc(&d_lik, (size_t)nstepK * nd * 8));
+    XCK(cudaMemcpy(d_masks, masks.data(), (size_t)nstates * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_pst, pst.data(), (size_t)npst * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_prior, prior.data(), (size_t)npst * 4, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_K, Kg.data(), (size_t)nstepK * 8, cudaMemcpyHostToDevice));
+    XCK(cudaMemcpy(d_d, dg.data(), (size_t)nd * 8, cudaMemcpyHostToDevice));
+    k_exact_S<<<(nstates + 127) / 128, 128>>>(d_masks, nstates, n, a, d, d_S);
+    XCK(cudaGetLastError());
+    XCK(cudaFuncSetAttribute(k_exact_variant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_exact_variant<<<nstepK * nd, 256, smem>>>(n, d_S, a, eB, cB, d_K, variant == 2 ? d_d : nullptr, nd, variant, ts, tdis, d_pst,
+                                                d_prior, (int)npst, d_lik);
+    XCK(cudaGetLastError());
+    XCK(cudaMemcpy(lik_out, d_lik, (size_t)nstepK * nd * 8, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_masks); cudaFree(d_pst); cudaFree(d_prior); cudaFree(d_S); cudaFree(d_K); cudaFree(d_d); cudaFree(d_lik);
     return rc;
 }
 

@@ -156,6 +156,14 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
     const Trans<float> tr = make_trans<float>(par[c], era ? era[t] : 0);
     const float cK = tr.c * tr.Kt;
     const float nal2e = alpha_pre<float>(par[c].alpha);
+    // external source (loss.c:93-101, future.c:90-97): C = c (K S + Ksrc g_q) = cK (S + (Ksrc/K) g_q).  The
+    // per-target offset is folded into the stored S for the duration of the scan and removed on write-back.
+    const double src_scale = tr.src ? (double)tr.Ks / (double)tr.Kt : 0.0;
+    auto src_offset = [&](int q) -> double {
+        if (!tr.src) return 0.0;
+        const double u = ls.src_unit ? ls.src_unit[q] : (double)(q + 1);
+        return src_scale * exp(-(par[c].alpha * u) * par[c].dsrc);
+    };
     uint8_t *yt = y + ((size_t)c * ntrans + t) * n;
     const uint8_t *zn = z + ((size_t)c * T + t + 1) * n;
     double *St = S + ((size_t)c * ntrans + t) * n;
@@ -168,7 +176,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < n) {
             if (GEOM == MP_GEOM_COORDS) { v.z = ls.px[q]; v.w = ls.py[q]; }
-            const double s = St[q];
+            const double s = St[q] + src_offset(q);
             v.x = (float)s; v.y = (float)(s - (double)v.x);
             const uint32_t yq = yt[q] != 0, zq = zn[q] != 0;
             ybits |= yq << j; Amask |= ((yq ^ 1u) & zq) << j; Bmask |= ((yq ^ 1u) & (zq ^ 1u)) << j;
@@ -277,7 +285,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
                 if (!(a || b)) continue;
                 const float4 tq = sT[tid + j * NT];
                 const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * 1024, tq.z, tq.w, drow);
-                const float sa = zero_after ? 0.f : fmaxf(fmaf(sgn, w, tq.x) + tq.y, 0.f);
+                const float sa = zero_after ? (float)src_offset(g + j * 1024) : fmaxf(fmaf(sgn, w, tq.x) + tq.y, 0.f);
                 acc2 += ldiff<float>(Num<float>::lg2(col_factor(cK, sa, a, b)), Num<float>::lg2(col_factor(cK, tq.x, a, b)));
             }
             if (own) {
@@ -304,7 +312,8 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
                     const float lo2 = tq.y + e;
                     hi = s + lo2;
                     float lo = lo2 - (hi - s);
-                    if (zero_after || hi < 0.f) { hi = 0.f; lo = 0.f; }
+                    if (zero_after) { const double so = src_offset(g + j * 1024); hi = (float)so; lo = (float)(so - (double)hi); }
+                    else if (hi < 0.f) { hi = 0.f; lo = 0.f; }
                     *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
                 }
                 P *= col_factor(cK, hi, (Amask >> j) & 1u, (Bmask >> j) & 1u);
@@ -324,7 +333,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         const int q = g + j * 1024;
         if (q < n) {
             const float4 tq = sT[tid + j * NT];
-            St[q] = (double)tq.x + (double)tq.y;
+            St[q] = fmax(((double)tq.x + (double)tq.y) - src_offset(q), 0.0);
             yt[q] = (uint8_t)((ybits >> j) & 1u);
         }
     }

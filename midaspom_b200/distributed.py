@@ -54,7 +54,7 @@ def ess_geyer(x: np.ndarray) -> float:
     """Effective sample size of one chain (Geyer initial positive sequence)."""
     x = np.asarray(x, dtype=float)
     n = len(x)
-    if n < 8 or x.std() < 1e-300:
+    if n < 8 or not np.isfinite(x).all() or x.var() <= 0.0 or (x - x.mean()).var() <= 0.0:
         return float(n)
     xc = x - x.mean()
     f = np.fft.rfft(xc, 2 * n)

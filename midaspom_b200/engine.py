@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "mp_set_scales", "mp_get_scales", "mp_connectivity", "mp_get_connectivity", "mp_loglik", "mp_loglik_host",
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
-    "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble",
+    "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant",
 )
 
 
@@ -115,6 +115,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_exact_posterior.argtypes = [C.c_int, i8p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                      C.c_double, C.c_double, dp, dp, C.POINTER(C.c_int)]
     L.mp_exact_last_error.restype = C.c_char_p
+    L.mp_exact_variant.argtypes = [C.c_int, C.c_int, i8p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp]
     _lib = L
     return L
 
@@ -375,3 +377,17 @@ def exact_posterior(obs, a=1.0 / 400.0, d=100.0, prior_occ=0.5, nstep=101, ecmin
     if rc != 0:
         raise MpError(f"mp_exact_posterior failed ({rc}): {lib.mp_exact_last_error().decode()}")
     return ll, ltot.value, dict(nvar=info[0], nstates=info[1], nextid=info[2], max_states_per_year=info[3])
+
+
+def exact_variant(variant, first_row, eB, cB, ts=20, tdis=10, a=1.0 / 400.0, d=200.0, prior_occ=0.5, nstepK=151, Kmin=0.1,
+                  Kmax=100.0, nstepd=20, dmin=200.0, dmax=4000.0, device=0):
+    """mp_exact_variant: MIDASPOM_dieoff.out ("dieoff") / MIDASPOM_loss.out ("loss") likelihood grids on the GPU."""
+    lib = load_library()
+    v = {"dieoff": 1, "loss": 2}[variant]
+    row = np.ascontiguousarray(first_row, dtype=np.int8)
+    out = np.zeros((nstepK, nstepd if v == 2 else 1))
+    rc = lib.mp_exact_variant(device, v, _p(row, _i8p), len(row), float(a), float(d), float(prior_occ), float(eB), float(cB), int(ts),
+                              int(tdis), int(nstepK), float(Kmin), float(Kmax), int(nstepd), float(dmin), float(dmax), _p(out, _dp))
+    if rc != 0:
+        raise MpError(f"mp_exact_variant failed ({rc}): {lib.mp_exact_last_error().decode()}")
+    return out[:, 0] if v == 1 else out

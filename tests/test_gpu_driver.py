@@ -78,3 +78,28 @@ def test_future_driver_matches_reference_runs(golden, tmp_path, tag, extra):
     assert (np.abs(got - mu) < 5 * sd + 3).all()
     if not extra:
         assert (np.diff(got) >= 0).all()                                               # extinction is absorbing without a source
+
+
+def test_variant_drivers_and_hypothesis_numbers(golden, tmp_path):
+    """run_examples.sh:11,14 with the reference's flags; then the AIC / Bayes-factor numbers of
+    Rscript/hypothesis_test.R:29-46 computed from the two files."""
+    build_drivers()
+    run("midaspom_dieoff", ["-a", 10, "-e", 0.71, "-c", 0.52, "-m", 400, "-d", 100, "-s", 151, "-i", EXAMPLE, "-o", tmp_path / "lh_dieoff.txt"])
+    run("midaspom_loss", ["-a", 10, "-e", 0.71, "-c", 0.52, "-m", 400, "-d", 100, "-s", 7, "-v", 3, "-i", EXAMPLE, "-o", tmp_path / "lh_loss.txt"])
+    die = np.array([float(v) for v in (tmp_path / "lh_dieoff.txt").read_text().split()])
+    loss = read_table(tmp_path / "lh_loss.txt")
+    np.testing.assert_allclose(die, golden["dieoff_s151"], rtol=1e-9, atol=5.1e-21)   # reference prints %.20lf
+    np.testing.assert_allclose(loss, golden["loss_s7v3"], rtol=1e-9, atol=5.1e-21)
+    assert (tmp_path / "lh_dieoff.txt").read_text().count("\n") == 0 and (tmp_path / "lh_loss.txt").read_text().count("\n") == 7
+    out = run("midaspom_hypothesis", [tmp_path / "lh_dieoff.txt", tmp_path / "lh_loss.txt", 8, 0.1, 100])
+    got = {" ".join(l.split()[:-1]): float(l.split()[-1]) for l in out.splitlines()}
+    Kd = 10 ** np.linspace(-1, 2, 151)
+    i1 = int(np.argmin(np.abs(Kd - 1.0)))                       # K = 1 is a node of the 151-point grid (index 50)
+    null = golden["dieoff_s151"][i1]
+    want = {"AIC H0": 2 - 2 * np.log(null / 2 ** 8), "AIC H1": 4 - 2 * np.log(golden["dieoff_s151"].max() / 2 ** 8),
+            "AIC H2": 6 - 2 * np.log(golden["loss_s7v3"].max() / 2 ** 8),
+            "log10BF H0vsH1": np.log10(null / (golden["dieoff_s151"].sum() / 7)),
+            "log10BF H0vsH2": np.log10(null / (golden["loss_s7v3"].sum() / 7 / 3)),
+            "log10BF H1vsH2": np.log10(golden["dieoff_s151"].sum() / (golden["loss_s7v3"].sum() / 3))}
+    for k, v in want.items():
+        assert abs(got[k] - v) < 1e-6 * max(1.0, abs(v)), (k, got[k], v)

@@ -173,6 +173,15 @@ def test_exact_engine_reproduces_reference_posterior_tables(golden, example_obs)
     np.testing.assert_allclose(ll3, golden["loglik_s3_survey"], rtol=0, atol=2e-12)
 
 
+def test_exact_variants_reproduce_dieoff_and_loss_outputs(golden, example_obs):
+    """run_examples.sh:11,14 -- `MIDASPOM_dieoff.out -a 10 -e 0.71 -c 0.52 -m 400 -d 100 -s 151` (151 values) and
+    `MIDASPOM_loss.out ... -s 7 -v 3` (7 x 3): vector propagation here vs matrix powers there."""
+    got = mb.exact_variant("dieoff", example_obs[0], 0.71, 0.52, ts=20, tdis=10, a=A, d=100.0, nstepK=151)
+    np.testing.assert_allclose(got, golden["dieoff_s151"], rtol=1e-9, atol=5.1e-21)   # reference prints %.20lf
+    got = mb.exact_variant("loss", example_obs[0], 0.71, 0.52, ts=20, tdis=10, a=A, d=100.0, nstepK=7, nstepd=3)
+    np.testing.assert_allclose(got, golden["loss_s7v3"], rtol=1e-9, atol=5.1e-21)
+
+
 def test_exact_engine_matches_oracle_marginal_on_random_small_landscapes():
     """Random 6-10 patch histories with missing cells (also in year 0, where the reference itself
     reads uninitialised memory): exact engine == oracle's forward recursion."""
@@ -245,9 +254,10 @@ def test_fp64_sweeps_follow_the_cpu_twin(geom, detect, sample_ab):
     rel_close(Sg, ch.S, 1e-9, floor=1e-9)
 
 
-@pytest.mark.parametrize("geom,n,C,T", [(O.GEOM_COORDS, 700, 3, 6), (O.GEOM_LINEAR, 2100, 2, 4), (O.GEOM_DENSE, 300, 5, 5),
-                                         (O.GEOM_COORDS, 1500, 19, 9)])
-def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T):
+@pytest.mark.parametrize("geom,n,C,T,variant", [(O.GEOM_COORDS, 700, 3, 6, None), (O.GEOM_LINEAR, 2100, 2, 4, None),
+                                                 (O.GEOM_DENSE, 300, 5, 5, None), (O.GEOM_COORDS, 1500, 19, 9, None),
+                                                 (O.GEOM_COORDS, 900, 4, 7, "dieoff"), (O.GEOM_LINEAR, 600, 3, 6, "loss")])
+def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T, variant):
     """The FP32 throughput sweep (cluster-split, two-float S, product-of-factors logs) draws from the
     same thresholds as the FP64 path: after one sweep from the same state the latent states agree
     except where a log-odds lies within FP32 rounding of its threshold, S agrees to 1e-5, and the
@@ -255,6 +265,9 @@ def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T):
     rng = np.random.default_rng(500 + n)
     spec, z, y = random_landscape(rng, n, T, geom, occ=0.5, miss=0.05)
     par = pdict(e=0.35, c=0.02 if geom != O.GEOM_LINEAR else 0.2, alpha=1 / 400, b=0.5)
+    if variant:                                                   # pre-event years with the dieoff / loss terms
+        spec["era"] = (np.arange(T - 1) < (T - 1) // 2).astype(np.uint8)
+        par.update(dict(K=2.2) if variant == "dieoff" else dict(K=1.0, Ksrc=4.0, dsrc=3.0))
     sc = mb.engine.sampler_config(sample_e=0, sample_c=0, update_z=0, n_adapt=0)
     out = {}
     for prec in (mb.FP64, mb.FP32):
