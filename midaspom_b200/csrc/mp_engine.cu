@@ -129,12 +129,13 @@ static int launch_sweep_y_fast(mp_engine *h)
         CK(cudaGetLastError());
     }
     Timed tm(h, MP_K_SWEEP_Y);
-    const int ept = (n + 1023) / 1024;                 // targets per thread (1024 threads per task)
+    int tpt = h->fast_tpt ? h->fast_tpt : (n > 6144 ? 512 : 1024);   // threads per task
+    if ((n + tpt - 1) / tpt > 31) tpt = 1024;
     const int cs = pick_cluster(C * ntrans, h->sm_count, 8);
     switch (h->geom) {
-    case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, ept, cs);
-    case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, ept, cs);
-    default: return mp_launch_sweep_fast_dense(h, ept, cs);
+    case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
+    case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);
+    default: return mp_launch_sweep_fast_dense(h, cs, tpt);
     }
 }
 template <typename R> static int launch_sweep_y(mp_engine *h)
@@ -298,6 +299,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     }
     mp_engine *h = new mp_engine();
     h->cfg = *cfg;
+    if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024) h->fast_tpt = v; }
     h->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char *what, cudaError_t ce) {
         g_create_error = std::string("mp_create: ") + what + ": " + cudaGetErrorString(ce);

@@ -49,6 +49,7 @@ struct mp_engine {
     int *d_cand_count = nullptr;     // [task][2]: candidates, occupied
     bool any_src = false;            // some chain has an external source term (Ksrc != 0)
     int sm_count = 148;
+    int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
     // timing
     bool timing = false;
     struct Span { cudaEvent_t a, b; int cat; };
@@ -120,6 +121,6 @@ template <typename R> inline mp::Landscape<R> view(const mp_engine *h)
 
 
 // FP32 fast sweep (mp_sweep_fast_*.cu, one translation unit per geometry)
-int mp_launch_sweep_fast_linear(mp_engine *h, int ept, int cs);
-int mp_launch_sweep_fast_coords(mp_engine *h, int ept, int cs);
-int mp_launch_sweep_fast_dense(mp_engine *h, int ept, int cs);
+int mp_launch_sweep_fast_linear(mp_engine *h, int cs, int tpt);
+int mp_launch_sweep_fast_coords(mp_engine *h, int cs, int tpt);
+int mp_launch_sweep_fast_dense(mp_engine *h, int cs, int tpt);

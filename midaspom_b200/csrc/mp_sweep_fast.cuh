@@ -137,13 +137,13 @@ __device__ __forceinline__ float col_factor(float cK, float s, bool a, bool b)
     return f;
 }
 
-template <int GEOM, int CS, int U>
-__global__ void __launch_bounds__(1024 / CS, CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
+template <int GEOM, int CS, int U, int TPT>
+__global__ void __launch_bounds__(TPT / CS, CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uint8_t *__restrict__ era,
                const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
                const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept)
 {
-    constexpr int NT = 1024 / CS, NW = NT / 32;         // CS * NW == 32 partial sums per flip
+    constexpr int NT = TPT / CS, NW = NT / 32, NSLOT = TPT / 32;   // NSLOT = CS * NW partial sums per flip (<= 32)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[2][2][32];                    // [round: fast, careful][parity][cluster rank * NW + warp]
     __shared__ __align__(8) unsigned long long mbar[2][2];
@@ -168,11 +168,11 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
     const uint8_t *zn = z + ((size_t)c * T + t + 1) * n;
     double *St = S + ((size_t)c * ntrans + t) * n;
 
-    // own targets: q_j = g + 1024 j, g = rank * NT + tid.  Amask: y=0,z'=1 ; Bmask: y=0,z'=0 ; ybits: y
+    // own targets: q_j = g + TPT j, g = rank * NT + tid.  Amask: y=0,z'=1 ; Bmask: y=0,z'=0 ; ybits: y
     const int g = (int)rank * NT + tid;
     uint32_t Amask = 0, Bmask = 0, ybits = 0;
     for (int j = 0; j < ept; j++) {
-        const int q = g + j * 1024;
+        const int q = g + j * TPT;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < n) {
             if (GEOM == MP_GEOM_COORDS) { v.z = ls.px[q]; v.w = ls.py[q]; }
@@ -209,6 +209,10 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         __syncthreads();
         cluster_barrier();                              // barriers initialised and every CTA running before remote stores
     }
+    // DSMEM addresses of this lane's destination CTA (lane < CS): red[0][0][0] and mbar[0][0] of CTA `lane`
+    const uint32_t red_remote = CS > 1 ? map_to_rank(smem_u32(&red[0][0][0]), (uint32_t)(lane < CS ? lane : 0)) : 0u;
+    const uint32_t bar_remote = CS > 1 ? map_to_rank(smem_u32(&mbar[0][0]), (uint32_t)(lane < CS ? lane : 0)) : 0u;
+    const uint32_t bar_local = smem_u32(&mbar[0][0]);
     const int ncand = count[2 * task];
     int nocc = count[2 * task + 1];
     const CandRec *recs = rec + (size_t)task * n;
@@ -220,17 +224,16 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         const int p = u & 1;
         v = warp_sum_f(v);
         if (CS > 1) {
-            const uint32_t bar = smem_u32(&mbar[round][p]);
-            if (tid == 0) mbar_expect_tx(bar, 128);     // 32 slots x 4 bytes land on this CTA
-            if (lane < CS)
-                st_async_f32(map_to_rank(smem_u32(&red[round][p][rank * NW + wid]), (uint32_t)lane), v,
-                             map_to_rank(bar, (uint32_t)lane));
-            mbar_wait(bar, (u >> 1) & 1u);
+            const uint32_t boff = (uint32_t)(round * 2 + p) * 8u;                       // &mbar[round][p] - &mbar[0][0]
+            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)rank * NW + wid) * 4u;   // &red[round][p][slot] - &red[0][0][0]
+            if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 4);  // NSLOT slots x 4 bytes land on this CTA
+            if (lane < CS) st_async_f32(red_remote + roff, v, bar_remote + boff);
+            mbar_wait(bar_local + boff, (u >> 1) & 1u);
         } else {
             if (lane == 0) red[round][p][wid] = v;
             __syncthreads();
         }
-        return warp_sum_f(red[round][p][lane]);
+        return warp_sum_f(lane < NSLOT ? red[round][p][lane] : 0.f);
     };
 
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;     // current record as two 16-byte halves
@@ -245,8 +248,8 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         const bool zero_after = (nocc + (cur ? -1 : 1)) == 0;
         const float sgn = cur ? -1.f : 1.f;
         const float *drow = GEOM == MP_GEOM_DENSE ? ls.dist + (size_t)k * n : nullptr;
-        const bool own = k >= g && ((k - g) & 1023) == 0;
-        const int kj = own ? (k - g) >> 10 : 31;         // slot of k if this thread owns it (bit 31 is never a valid slot... ept <= 31)
+        const bool own = k >= g && (k - g) % TPT == 0;
+        const int kj = own ? (k - g) / TPT : 31;         // slot of k if this thread owns it (bit 31 is never a valid slot... ept <= 31)
         const uint32_t ownbit = own ? 1u << kj : 0u;
         const uint32_t Ae = Amask & ~ownbit, Be = Bmask;  // a candidate has z'=1: it can only be in class A
 
@@ -256,7 +259,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
             float acc2 = -D, P = 1.f;
             auto eval_one = [&](int j) {
                 const float4 tq = sT[tid + j * NT];
-                const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * 1024, tq.z, tq.w, drow);
+                const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * TPT, tq.z, tq.w, drow);
                 const float sa = fmaxf(fmaf(sgn, w, tq.x) + tq.y, 0.f);
                 P *= col_factor(cK, sa, (Ae >> j) & 1u, (Be >> j) & 1u);
             };
@@ -284,8 +287,8 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
                 const bool a = (Ae >> j) & 1u, b = (Be >> j) & 1u;
                 if (!(a || b)) continue;
                 const float4 tq = sT[tid + j * NT];
-                const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * 1024, tq.z, tq.w, drow);
-                const float sa = zero_after ? (float)src_offset(g + j * 1024) : fmaxf(fmaf(sgn, w, tq.x) + tq.y, 0.f);
+                const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * TPT, tq.z, tq.w, drow);
+                const float sa = zero_after ? (float)src_offset(g + j * TPT) : fmaxf(fmaf(sgn, w, tq.x) + tq.y, 0.f);
                 acc2 += ldiff<float>(Num<float>::lg2(col_factor(cK, sa, a, b)), Num<float>::lg2(col_factor(cK, tq.x, a, b)));
             }
             if (own) {
@@ -304,33 +307,40 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
             float Dn = 0.f, P = 1.f;
             auto commit_one = [&](int j) {
                 const float4 tq = sT[tid + j * NT];
-                float hi = tq.x;
-                if (j != kj) {                           // S_k does not contain y_k
-                    const float a = sgn * fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * 1024, tq.z, tq.w, drow);
-                    const float s = tq.x + a, bb = s - tq.x;
-                    const float e = (tq.x - (s - bb)) + (a - bb);   // exact rounding error of hi + a
-                    const float lo2 = tq.y + e;
-                    hi = s + lo2;
-                    float lo = lo2 - (hi - s);
-                    if (zero_after) { const double so = src_offset(g + j * 1024); hi = (float)so; lo = (float)(so - (double)hi); }
-                    else if (hi < 0.f) { hi = 0.f; lo = 0.f; }
-                    *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
-                }
+                const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * TPT, tq.z, tq.w, drow);
+                const float a = j == kj ? 0.f : sgn * w;               // S_k does not contain y_k
+                const float s = tq.x + a, bb = s - tq.x;
+                const float e = (tq.x - (s - bb)) + (a - bb);           // exact rounding error of hi + a
+                const float lo2 = tq.y + e;
+                float hi = s + lo2, lo = lo2 - (hi - s);
+                if (hi < 0.f) { hi = 0.f; lo = 0.f; }
+                *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
                 P *= col_factor(cK, hi, (Amask >> j) & 1u, (Bmask >> j) & 1u);
             };
-            int j = 0;
-            for (; j + U <= ept; j += U) {
+            if (!zero_after) {
+                int j = 0;
+                for (; j + U <= ept; j += U) {
 #pragma unroll
-                for (int u = 0; u < U; u++) commit_one(j + u);
-                Dn += Num<float>::lg2(P); P = 1.f;
+                    for (int u = 0; u < U; u++) commit_one(j + u);
+                    Dn += Num<float>::lg2(P); P = 1.f;
+                }
+                if (j < ept) { for (; j < ept; j++) commit_one(j); Dn += Num<float>::lg2(P); }
+            } else {
+                // the last occupied patch left: every S is exactly its external-source offset
+                for (int j = 0; j < ept; j++) {
+                    const double so = src_offset(g + j * TPT);
+                    const float hi = (float)so, lo = (float)(so - (double)hi);
+                    *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
+                    P = col_factor(cK, hi, (Amask >> j) & 1u, (Bmask >> j) & 1u);
+                    Dn += Num<float>::lg2(P);
+                }
             }
-            if (j < ept) { for (; j < ept; j++) commit_one(j); Dn += Num<float>::lg2(P); }
             D = Dn;
         }
         r0 = n0; r1 = n1;
     }
     for (int j = 0; j < ept; j++) {
-        const int q = g + j * 1024;
+        const int q = g + j * TPT;
         if (q < n) {
             const float4 tq = sT[tid + j * NT];
             St[q] = fmax(((double)tq.x + (double)tq.y) - src_offset(q), 0.0);
@@ -346,12 +356,12 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
 #ifdef MP_FAST_GEOM
 #include "mp_host.h"
 namespace mp {
-template <int CS, int U> static int launch_fast(mp_engine *h, int ept)
+template <int CS, int U, int TPT> static int launch_fast(mp_engine *h, int ept)
 {
-    constexpr int NT = 1024 / CS;
+    constexpr int NT = TPT / CS;
     const size_t smem = (size_t)ept * NT * 16;
     REQUIRE(smem <= 227 * 1024 && ept <= 31, MP_ERR_UNSUPPORTED, "n_patches too large for the fast y sweep");
-    auto kern = k_sweep_y_fast<MP_FAST_GEOM, CS, U>;
+    auto kern = k_sweep_y_fast<MP_FAST_GEOM, CS, U, TPT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(h->cfg.n_chains * (h->cfg.n_years - 1) * CS));
@@ -367,17 +377,26 @@ template <int CS, int U> static int launch_fast(mp_engine *h, int ept)
                           (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept));
     return MP_OK;
 }
-template <int CS> static int launch_fast_u(mp_engine *h, int ept)
+template <int CS, int TPT> static int launch_fast_u(mp_engine *h, int ept)
 {
-    return ept % 5 == 0 ? launch_fast<CS, 5>(h, ept) : launch_fast<CS, 4>(h, ept);
+    return ept % 5 == 0 ? launch_fast<CS, 5, TPT>(h, ept) : launch_fast<CS, 4, TPT>(h, ept);
 }
-static int launch_fast_any(mp_engine *h, int ept, int cs)
+// tpt = threads per task: 1024 for small landscapes; 512 for large ones (fewer warps pay the
+// per-flip bookkeeping and reduction, each thread carries more independent targets)
+static int launch_fast_any(mp_engine *h, int cs, int tpt)
 {
+    const int ept = (h->cfg.n_patches + tpt - 1) / tpt;
+    if (tpt == 512) switch (cs) {
+        case 1: return launch_fast_u<1, 512>(h, ept);
+        case 2: return launch_fast_u<2, 512>(h, ept);
+        case 4: return launch_fast_u<4, 512>(h, ept);
+        default: return launch_fast_u<8, 512>(h, ept);
+    }
     switch (cs) {
-    case 1: return launch_fast_u<1>(h, ept);
-    case 2: return launch_fast_u<2>(h, ept);
-    case 4: return launch_fast_u<4>(h, ept);
-    default: return launch_fast_u<8>(h, ept);
+    case 1: return launch_fast_u<1, 1024>(h, ept);
+    case 2: return launch_fast_u<2, 1024>(h, ept);
+    case 4: return launch_fast_u<4, 1024>(h, ept);
+    default: return launch_fast_u<8, 1024>(h, ept);
     }
 }
 }  // namespace mp

@@ -2,4 +2,4 @@
 #include "../../include/libmidaspom_cuda.h"
 #define MP_FAST_GEOM MP_GEOM_LINEAR
 #include "mp_sweep_fast.cuh"
-int mp_launch_sweep_fast_linear(mp_engine *h, int ept, int cs) { return mp::launch_fast_any(h, ept, cs); }
+int mp_launch_sweep_fast_linear(mp_engine *h, int cs, int tpt) { return mp::launch_fast_any(h, cs, tpt); }
