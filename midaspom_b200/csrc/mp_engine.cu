@@ -37,7 +37,7 @@ static int launch_pack_y(mp_engine *h)
     CK(cudaGetLastError());
     return MP_OK;
 }
-template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int nsets)
+template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_base, int nsets)
 {
     Timed tm(h, MP_K_CONN);
     ConnArgs<R> a;
@@ -45,7 +45,7 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int nsets
     a.par[0] = h->d_par; a.par[1] = h->d_prop;
     a.aw[0] = (const R *)h->d_aw[0]; a.aw[1] = (const R *)h->d_aw[1];
     a.S[0] = h->d_S[0]; a.S[1] = h->d_S[1];
-    a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords;
+    a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords; a.set_base = set_base;
     dim3 grid((h->cfg.n_patches + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
     const int ny = a.ntrans;
     if (ny <= 8) k_conn<R, GEOM, 8><<<grid, CONN_TILE, 0, h->stream>>>(a);
@@ -55,12 +55,14 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int nsets
     CK(cudaGetLastError());
     return MP_OK;
 }
-template <typename R> static int launch_conn(mp_engine *h, int nsets)
+// sets [set_base, set_base + nsets): 0 = resident parameters -> S, 1 = proposal -> S_prop
+template <typename R> static int launch_conn(mp_engine *h, int set_base, int nsets)
 {
+    if (nsets <= 0) return MP_OK;
     switch (h->geom) {
-    case MP_GEOM_LINEAR: return launch_conn_g<R, MP_GEOM_LINEAR>(h, nsets);
-    case MP_GEOM_COORDS: return launch_conn_g<R, MP_GEOM_COORDS>(h, nsets);
-    default: return launch_conn_g<R, MP_GEOM_DENSE>(h, nsets);
+    case MP_GEOM_LINEAR: return launch_conn_g<R, MP_GEOM_LINEAR>(h, set_base, nsets);
+    case MP_GEOM_COORDS: return launch_conn_g<R, MP_GEOM_COORDS>(h, set_base, nsets);
+    default: return launch_conn_g<R, MP_GEOM_DENSE>(h, set_base, nsets);
     }
 }
 // colonisation log-likelihood partials: set s uses parameters par_s, connectivity S_s, writes partial[s]
@@ -109,7 +111,7 @@ static int pick_cluster(int tasks, int sms, int max_cs)
     int best = 1; double best_cost = 1e30;
     for (int cs = 1; cs <= max_cs; cs *= 2) {
         const int ctas = tasks * cs;
-        const double cost = (double)((ctas + sms - 1) / sms) / cs * (1.0 + 0.02 * cs);
+        const double cost = (double)((ctas + sms - 1) / sms) / cs * (1.0 + 0.08 * cs);   // measured: DSMEM sync cost grows with CS
         if (cost < best_cost - 1e-9) { best_cost = cost; best = cs; }
     }
     return best;
@@ -131,7 +133,7 @@ static int launch_sweep_y_fast(mp_engine *h)
     Timed tm(h, MP_K_SWEEP_Y);
     int tpt = h->fast_tpt ? h->fast_tpt : (n > 6144 ? 512 : 1024);   // threads per task
     if ((n + tpt - 1) / tpt > 31) tpt = 1024;
-    const int cs = pick_cluster(C * ntrans, h->sm_count, 8);
+    const int cs = h->fast_cs ? h->fast_cs : pick_cluster(C * ntrans, h->sm_count, 8);
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
     case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);
@@ -166,7 +168,9 @@ template <typename R> static int refresh_S(mp_engine *h)
     int rc;
     if ((rc = launch_pack_y(h)) != MP_OK) return rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
-    return launch_conn<R>(h, 1);
+    const int rc2 = launch_conn<R>(h, 0, 1);
+    if (rc2 == MP_OK) h->S_valid = true;
+    return rc2;
 }
 // per-chain complete-data log-likelihood of the resident state, using the resident S
 template <typename R> static int loglik_resident(mp_engine *h, double *d_draw_row, double *d_parts)
@@ -198,7 +202,11 @@ template <typename R> static int sweep_once(mp_engine *h)
           CK(cudaGetLastError()); }
         if ((rc = launch_area_weights<R>(h, 1)) != MP_OK) return rc;
     }
-    if ((rc = launch_conn<R>(h, do_ab ? 2 : 1)) != MP_OK) return rc;
+    // The resident S is maintained by exact rank-1 updates; the FP32 engine recomputes it from scratch only
+    // every MP_REFRESH_EVERY sweeps (the FP64 parity engine every sweep, like the CPU twin).
+    const bool refresh = is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0 || !h->S_valid;
+    if ((rc = launch_conn<R>(h, refresh ? 0 : 1, (refresh ? 1 : 0) + (do_ab ? 1 : 0))) != MP_OK) return rc;
+    h->S_valid = true;
     if ((rc = launch_col<R>(h, do_ab ? 2 : 1, h->d_par, h->d_S[0], h->d_prop, h->d_S[1])) != MP_OK) return rc;
     { Timed tm(h, MP_K_SMALL);
       k_decide_ab<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
@@ -299,6 +307,8 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     }
     mp_engine *h = new mp_engine();
     h->cfg = *cfg;
+    if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
+    if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024) h->fast_tpt = v; }
     h->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char *what, cudaError_t ce) {
@@ -365,7 +375,7 @@ int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
     REQUIRE(spacing > 0.0, MP_ERR_ARG, "spacing must be positive");
     h->geom = MP_GEOM_LINEAR; h->spacing = spacing;
     int rc = set_area(h, area);
-    if (rc == MP_OK) h->have_landscape = true;
+    if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;
 }
 int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, const double *area)
@@ -378,7 +388,7 @@ int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, cons
     if ((rc = upload_real(h, h->d_px, x, nN(h))) != MP_OK) return rc;
     if ((rc = upload_real(h, h->d_py, y, nN(h))) != MP_OK) return rc;
     rc = set_area(h, area);
-    if (rc == MP_OK) h->have_landscape = true;
+    if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;
 }
 int mp_set_landscape_dense(mp_engine *h, const double *dist, const double *area)
@@ -392,7 +402,7 @@ int mp_set_landscape_dense(mp_engine *h, const double *dist, const double *area)
     int rc;
     if ((rc = upload_real(h, h->d_dist, dist, nn)) != MP_OK) return rc;
     rc = set_area(h, area);
-    if (rc == MP_OK) h->have_landscape = true;
+    if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;
 }
 int mp_set_source_units(mp_engine *h, const double *src_unit)
@@ -432,7 +442,7 @@ int mp_set_params(mp_engine *h, const mp_params *par)
     if (!h || !par) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
     for (size_t c = 0; c < nC(h); c++) REQUIRE(par[c].K > 0.0 && par[c].alpha > 0.0, MP_ERR_ARG, "need K > 0 and alpha > 0");
-    h->any_src = false;
+    h->any_src = false; h->S_valid = false;
     for (size_t c = 0; c < nC(h); c++) if (par[c].Ksrc != 0.0) h->any_src = true;
     CK(cudaMemcpyAsync(h->d_par, par, nC(h) * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -453,7 +463,7 @@ int mp_set_state(mp_engine *h, const uint8_t *z, const uint8_t *y)
     CK(cudaMemcpyAsync(h->d_z, z, nC(h) * zcells(h), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_y, y, nC(h) * ycells(h), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->have_state = true;
+    h->have_state = true; h->S_valid = false;
     return MP_OK;
 }
 int mp_get_state(mp_engine *h, uint8_t *z, uint8_t *y)

@@ -49,6 +49,9 @@ struct mp_engine {
     int *d_cand_count = nullptr;     // [task][2]: candidates, occupied
     bool any_src = false;            // some chain has an external source term (Ksrc != 0)
     int sm_count = 148;
+    int refresh_every = 16;          // FP32 engine: sweeps between from-scratch recomputations of the resident S
+    bool S_valid = false;            // resident S corresponds to the resident (y, alpha, b)
+    int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides
     int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
     // timing
     bool timing = false;

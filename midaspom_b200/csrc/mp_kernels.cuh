@@ -61,6 +61,7 @@ template <typename R> struct ConnArgs {
     double *S[2];
     const uint32_t *ybits;
     int ntrans, nwords;
+    int set_base;          // first parameter set of this launch (blockIdx.z counts from it)
 };
 
 template <typename R, int GEOM, int NYB>
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
     __shared__ R sx[CONN_TILE], sy[CONN_TILE], saw[CONN_TILE];
     __shared__ uint32_t sbits[CONN_TILE];
     __shared__ __align__(16) double sy01[CONN_TILE][NYB];
-    const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
+    const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z + a.set_base, tid = threadIdx.x;
     const int kbase = blockIdx.x * CONN_TILE * CONN_TGT + tid;
     const mp_params *parp = set ? a.par[1] : a.par[0];
     const R apre = alpha_pre<R>(parp[c].alpha);

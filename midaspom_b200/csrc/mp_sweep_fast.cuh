@@ -138,7 +138,7 @@ __device__ __forceinline__ float col_factor(float cK, float s, bool a, bool b)
 }
 
 template <int GEOM, int CS, int U, int TPT>
-__global__ void __launch_bounds__(TPT / CS, CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
+__global__ void __launch_bounds__(TPT / CS, CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uint8_t *__restrict__ era,
                const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
                const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept)
@@ -260,7 +260,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
             auto eval_one = [&](int j) {
                 const float4 tq = sT[tid + j * NT];
                 const float w = fast_weight<GEOM>(ls, nal2e, lawk, k, kx, ky, g + j * TPT, tq.z, tq.w, drow);
-                const float sa = fmaxf(fmaf(sgn, w, tq.x) + tq.y, 0.f);
+                const float sa = fmaf(sgn, w, tq.x) + tq.y;            // a negative rounding residue saturates like 0 below
                 P *= col_factor(cK, sa, (Ae >> j) & 1u, (Be >> j) & 1u);
             };
             int j = 0;
@@ -363,6 +363,7 @@ template <int CS, int U, int TPT> static int launch_fast(mp_engine *h, int ept)
     REQUIRE(smem <= 227 * 1024 && ept <= 31, MP_ERR_UNSUPPORTED, "n_patches too large for the fast y sweep");
     auto kern = k_sweep_y_fast<MP_FAST_GEOM, CS, U, TPT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(h->cfg.n_chains * (h->cfg.n_years - 1) * CS));
     cfg.blockDim = dim3(NT);
@@ -390,12 +391,14 @@ static int launch_fast_any(mp_engine *h, int cs, int tpt)
         case 1: return launch_fast_u<1, 512>(h, ept);
         case 2: return launch_fast_u<2, 512>(h, ept);
         case 4: return launch_fast_u<4, 512>(h, ept);
+        case 16: return launch_fast_u<16, 512>(h, ept);
         default: return launch_fast_u<8, 512>(h, ept);
     }
     switch (cs) {
     case 1: return launch_fast_u<1, 1024>(h, ept);
     case 2: return launch_fast_u<2, 1024>(h, ept);
     case 4: return launch_fast_u<4, 1024>(h, ept);
+    case 16: return launch_fast_u<16, 1024>(h, ept);
     default: return launch_fast_u<8, 1024>(h, ept);
     }
 }
