@@ -625,10 +625,37 @@ int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
             for (size_t k = 0; k < N; k++) yc[t * N + k] = zc[t * N + k] && zc[(t + 1) * N + k];
     }
     if ((rc = mp_set_params(h, par.data())) != MP_OK) return rc;
-    if ((rc = mp_set_scales(h, lsig.data())) != MP_OK) return rc;
     if ((rc = mp_set_state(h, z.data(), y.data())) != MP_OK) return rc;
     h->sweep = 0; h->ndraws = 0;
-    return mp_connectivity(h, nullptr);
+    if ((rc = mp_connectivity(h, nullptr)) != MP_OK) return rc;
+    if (disperse) {
+        // a dispersed start must be a possible state: an empty cell next year (y=0, z'=0) needs C < 1, i.e.
+        // c < 1 / max(K_t S + Ksrc_t g); pull c below that bound (same rule as the CPU twin's spom_init_chain)
+        std::vector<double> S(C * (T - 1) * N), unit(N);
+        std::vector<uint8_t> era(T, 0);
+        CK(cudaMemcpy(S.data(), h->d_S[0], S.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(unit.data(), h->d_src_unit, N * 8, cudaMemcpyDeviceToHost));
+        if (h->have_era) CK(cudaMemcpy(era.data(), h->d_era, T - 1, cudaMemcpyDeviceToHost));
+        for (size_t c = 0; c < C; c++) {
+            mp_params &p = par[c];
+            double smax = 0.0;
+            for (size_t t = 0; t + 1 < T; t++) {
+                const bool pre = era[t] != 0, src = pre && p.Ksrc != 0.0;
+                for (size_t k = 0; k < N; k++) {
+                    const size_t i = t * N + k;
+                    if (y[c * (T - 1) * N + i] || z[c * T * N + i + N]) continue;
+                    const double g = src ? exp(-p.alpha * unit[k] * p.dsrc) : 0.0;
+                    const double v = pre ? p.K * S[c * (T - 1) * N + i] + p.Ksrc * g : S[c * (T - 1) * N + i];
+                    if (v > smax) smax = v;
+                }
+            }
+            if (smax > 0.0 && p.c * smax >= 1.0) { p.c = 0.5 / smax; if (p.c < sc->c_min) p.c = sc->c_min; }
+            lsig[c * MP_NLSIG + 1] = log(0.1 * p.c);
+        }
+        if ((rc = mp_set_params(h, par.data())) != MP_OK) return rc;
+        h->S_valid = true;                               // c does not enter S
+    }
+    return mp_set_scales(h, lsig.data());
 }
 int mp_sweep(mp_engine *h, int nsweeps)
 {

@@ -424,7 +424,6 @@ void spom_init_chain(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t 
         spom_rng(seed, chain, 0, RK_INIT_PARAM, 1, 0, r);
         if (cfg->sample_p) par->p = cfg->p_min + spom_u01(r[0]) * (cfg->p_max - cfg->p_min);
     }
-    lsig[0] = log(0.05); lsig[1] = log(0.1 * par->c); lsig[2] = log(0.05); lsig[3] = log(0.05); lsig[4] = log(0.05);
     for (int t = 0; t < T; t++)
         for (int k = 0; k < n; k++) {
             const int o = m->obs[(size_t)t * n + k];
@@ -439,6 +438,23 @@ void spom_init_chain(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t 
         for (int k = 0; k < n; k++)
             y[(size_t)t * n + k] = z[(size_t)t * n + k] && z[(size_t)(t + 1) * n + k];
     spom_refresh_S(m, par, y, S);
+    if (disperse) {
+        /* a dispersed start must be a possible state: an empty cell next year (y=0, z'=0) needs C < 1,
+         * i.e. c < 1 / max(K_t S + Ksrc_t g).  Pull c below that bound (no effect on feasible draws). */
+        double smax = 0.0;
+        for (int t = 0; t + 1 < T; t++) {
+            const int pre = is_pre(m, t), src = needs_src(par, pre);
+            for (int k = 0; k < n; k++) {
+                const size_t i = (size_t)t * n + k;
+                if (y[i] || z[i + n]) continue;
+                const double g = src ? spom_source_term(m, par, k) : 0.0;
+                const double v = pre ? par->K * S[i] + par->Ksrc * g : S[i];
+                if (v > smax) smax = v;
+            }
+        }
+        if (smax > 0.0 && par->c * smax >= 1.0) { par->c = 0.5 / smax; if (par->c < cfg->c_min) par->c = cfg->c_min; }
+    }
+    lsig[0] = log(0.05); lsig[1] = log(0.1 * par->c); lsig[2] = log(0.05); lsig[3] = log(0.05); lsig[4] = log(0.05);
 }
 
 /* Gibbs draws compare logit(u) with the log-odds: u < 1/(1+exp(-d))  <=>  log(u/(1-u)) < d */
