@@ -351,6 +351,9 @@ int mp_create(const mp_config *cfg, mp_engine **out)
 }
 
 // ---- landscape
+// Uploads below use the blocking default stream; the engine stream is non-blocking, so wait for its
+// pending work first (a setter called after an asynchronous mp_sweep must not race with it).
+static int quiesce(mp_engine *h) { CK(cudaStreamSynchronize(h->stream)); return MP_OK; }
 static int upload_real(mp_engine *h, void *dst, const double *src, size_t n)
 {
     if (is64(h)) { CK(cudaMemcpy(dst, src, n * 8, cudaMemcpyHostToDevice)); return MP_OK; }
@@ -372,6 +375,7 @@ int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
 {
     if (!h) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(spacing > 0.0, MP_ERR_ARG, "spacing must be positive");
     h->geom = MP_GEOM_LINEAR; h->spacing = spacing;
     int rc = set_area(h, area);
@@ -382,6 +386,7 @@ int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, cons
 {
     if (!h) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(x && y, MP_ERR_ARG, "null coordinates");
     h->geom = MP_GEOM_COORDS;
     int rc;
@@ -395,6 +400,7 @@ int mp_set_landscape_dense(mp_engine *h, const double *dist, const double *area)
 {
     if (!h) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(dist, MP_ERR_ARG, "null distance matrix");
     const size_t nn = nN(h) * nN(h);
     if (!h->d_dist) CK(cudaMalloc(&h->d_dist, nn * rsz(h)));
@@ -409,6 +415,7 @@ int mp_set_source_units(mp_engine *h, const double *src_unit)
 {
     if (!h) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     std::vector<double> u(nN(h));
     for (size_t k = 0; k < nN(h); k++) u[k] = src_unit ? src_unit[k] : (double)(k + 1);   // loss.c:365
     CK(cudaMemcpy(h->d_src_unit, u.data(), nN(h) * 8, cudaMemcpyHostToDevice));
@@ -431,6 +438,7 @@ int mp_set_era(mp_engine *h, const uint8_t *era)
 {
     if (!h) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     h->have_era = era != nullptr;
     if (era) CK(cudaMemcpy(h->d_era, era, nT(h) - 1, cudaMemcpyHostToDevice));
     return MP_OK;
@@ -479,6 +487,7 @@ int mp_set_scales(mp_engine *h, const double *lsig)
 {
     if (!h || !lsig) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     CK(cudaMemcpy(h->d_lsig, lsig, nC(h) * MP_NLSIG * 8, cudaMemcpyHostToDevice));
     return MP_OK;
 }
@@ -633,9 +642,11 @@ int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
         // c < 1 / max(K_t S + Ksrc_t g); pull c below that bound (same rule as the CPU twin's spom_init_chain)
         std::vector<double> S(C * (T - 1) * N), unit(N);
         std::vector<uint8_t> era(T, 0);
-        CK(cudaMemcpy(S.data(), h->d_S[0], S.size() * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(unit.data(), h->d_src_unit, N * 8, cudaMemcpyDeviceToHost));
-        if (h->have_era) CK(cudaMemcpy(era.data(), h->d_era, T - 1, cudaMemcpyDeviceToHost));
+        // the engine stream is non-blocking: copy on it (a default-stream cudaMemcpy would not wait for k_conn)
+        CK(cudaMemcpyAsync(S.data(), h->d_S[0], S.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(unit.data(), h->d_src_unit, N * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (h->have_era) CK(cudaMemcpyAsync(era.data(), h->d_era, T - 1, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
         for (size_t c = 0; c < C; c++) {
             mp_params &p = par[c];
             double smax = 0.0;
