@@ -16,7 +16,7 @@ eng.set_landscape_coords(wl['px'], wl['py'], wl['area']); eng.set_source_units(N
 eng.set_observations(wl['obs'])
 eng.set_params([bench.start_params(wl)] * C)
 kw = bench.sampler_kwargs(wl); kw['n_adapt'] = nsw // 4
-eng.init_chains(mb.engine.sampler_config(**kw), disperse=True)
+eng.init_chains(mb.engine.sampler_config(**kw), disperse=(len(sys.argv) > 3 and sys.argv[3] == "disperse"))
 t0 = time.time(); eng.sweep(nsw); dt = time.time() - t0
 d = eng.get_draws()
 half = d[nsw // 2:]
