@@ -140,6 +140,10 @@ def cpu_sample(wl, chains, budget_s, steps=1, warmup=0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.workload.startswith("cfg5"):
+        print(json.dumps(dict(impl="reference", unavailable="N=100,000: one connectivity evaluation is 1e10 pair terms (minutes per "
+                              "sweep on the host); no CPU arm for this workload")), flush=True)
+        return
     from midaspom_b200 import synth
     wl = synth.make_workload(args.workload)
     chains = wl["chains_per_gpu"] * max(1, args.gpus)

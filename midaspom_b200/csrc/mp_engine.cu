@@ -118,7 +118,7 @@ static int pick_cluster(int tasks, int sms, int max_cs)
 }
 static bool fast_sweep_ok(const mp_engine *h)
 {
-    return !is64(h) && h->cfg.n_patches <= 31 * 1024;
+    return !is64(h) && h->cfg.n_patches <= 113000;    // 2 N bytes of shared memory per CTA in a cluster of 8
 }
 static int launch_sweep_y_fast(mp_engine *h)
 {
@@ -133,7 +133,8 @@ static int launch_sweep_y_fast(mp_engine *h)
     Timed tm(h, MP_K_SWEEP_Y);
     int tpt = h->fast_tpt ? h->fast_tpt : (n > 6144 ? 512 : 1024);   // threads per task
     if ((n + tpt - 1) / tpt > 31) tpt = 1024;
-    const int cs = h->fast_cs ? h->fast_cs : pick_cluster(C * ntrans, h->sm_count, 8);
+    for (int big = 2048; (n + tpt - 1) / tpt > 31 && big <= 8192; big *= 2) tpt = big;   // N > 31k: 2048..8192 threads, cluster of 8
+    const int cs = tpt > 1024 ? 8 : (h->fast_cs ? h->fast_cs : pick_cluster(C * ntrans, h->sm_count, 8));
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
     case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);
@@ -309,7 +310,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     h->cfg = *cfg;
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
-    if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024) h->fast_tpt = v; }
+    if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
     h->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char *what, cudaError_t ce) {
         g_create_error = std::string("mp_create: ") + what + ": " + cudaGetErrorString(ce);

@@ -138,14 +138,17 @@ __device__ __forceinline__ float col_factor(float cK, float s, bool a, bool b)
 }
 
 template <int GEOM, int CS, int U, int TPT>
-__global__ void __launch_bounds__(TPT / CS, CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
+__global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uint8_t *__restrict__ era,
                const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
                const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept)
 {
-    constexpr int NT = TPT / CS, NW = NT / 32, NSLOT = TPT / 32;   // NSLOT = CS * NW partial sums per flip (<= 32)
+    constexpr int NT = TPT / CS, NW = NT / 32;
+    constexpr bool HIER = TPT / 32 > 32;                // more than 32 warps per task: reduce inside the CTA first
+    constexpr int NSLOT = HIER ? CS : TPT / 32;          // partial sums exchanged per flip (<= 32)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[2][2][32];                    // [round: fast, careful][parity][cluster rank * NW + warp]
+    __shared__ float wred[2][2][32];                   // HIER only: per-warp partials inside the CTA
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
@@ -223,16 +226,23 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
         const uint32_t u = uses[round]++;
         const int p = u & 1;
         v = warp_sum_f(v);
+        if (HIER) {                                     // CTA partial first (one __syncthreads), then CS partials over DSMEM
+            if (lane == 0) wred[round][p][wid] = v;
+            __syncthreads();
+            v = warp_sum_f(lane < NW ? wred[round][p][lane] : 0.f);
+        }
         if (CS > 1) {
             const uint32_t boff = (uint32_t)(round * 2 + p) * 8u;                       // &mbar[round][p] - &mbar[0][0]
-            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)rank * NW + wid) * 4u;   // &red[round][p][slot] - &red[0][0][0]
+            const uint32_t slot = HIER ? rank : rank * NW + wid;
+            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)slot) * 4u;    // &red[round][p][slot] - &red[0][0][0]
             if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 4);  // NSLOT slots x 4 bytes land on this CTA
-            if (lane < CS) st_async_f32(red_remote + roff, v, bar_remote + boff);
+            if (lane < CS && (!HIER || wid == 0)) st_async_f32(red_remote + roff, v, bar_remote + boff);
             mbar_wait(bar_local + boff, (u >> 1) & 1u);
-        } else {
-            if (lane == 0) red[round][p][wid] = v;
-            __syncthreads();
+            return warp_sum_f(lane < NSLOT ? red[round][p][lane] : 0.f);
         }
+        if (HIER) return v;                             // single CTA: the CTA partial is the total
+        if (lane == 0) red[round][p][wid] = v;
+        __syncthreads();
         return warp_sum_f(lane < NSLOT ? red[round][p][lane] : 0.f);
     };
 
@@ -387,6 +397,11 @@ template <int CS, int TPT> static int launch_fast_u(mp_engine *h, int ept)
 static int launch_fast_any(mp_engine *h, int cs, int tpt)
 {
     const int ept = (h->cfg.n_patches + tpt - 1) / tpt;
+    if (tpt > 1024) {                                   // large landscapes: clusters of 8, 256..1024 threads per CTA
+        if (tpt == 2048) return launch_fast_u<8, 2048>(h, ept);
+        if (tpt == 4096) return launch_fast_u<8, 4096>(h, ept);
+        return launch_fast_u<8, 8192>(h, ept);
+    }
     if (tpt == 512) switch (cs) {
         case 1: return launch_fast_u<1, 512>(h, ept);
         case 2: return launch_fast_u<2, 512>(h, ept);

@@ -16,6 +16,8 @@ WORKLOADS = {
     "cfg2": dict(n=1000, T=10, chains_per_gpu=8, detect=1, desc="synthetic N=1,000 x T=10, 8 chains, imperfect detection"),
     "cfg3": dict(n=10000, T=20, chains_per_gpu=8, detect=0, desc="synthetic N=10,000 x T=20, 64 chains over 8 GPUs (8 per GPU)"),
     "tiny": dict(n=256, T=6, chains_per_gpu=4, detect=0, desc="smoke-test size"),
+    "cfg5": dict(n=100000, T=30, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=30, one chain"),
+    "cfg5s": dict(n=40000, T=12, chains_per_gpu=1, detect=0, desc="synthetic N=40,000 x T=12, one chain (reduced cfg5)"),
 }
 TRUTH = dict(e=0.3, alpha=1.0 / 400.0, b=0.5, p_detect=0.8, target_mean_C=0.3)
 
@@ -33,9 +35,47 @@ def kernel_matrix(px, py, area, alpha, b, dtype=np.float32):
     return W
 
 
+def make_workload_large(name: str, seed: int = 12345, device: int = 0):
+    """Same generative model for landscapes whose N x N kernel matrix does not fit the host (cfg5):
+    the connectivity of each simulated year comes from the engine itself (mp_connectivity on a two-row
+    engine), the Bernoulli draws stay in numpy.  Needs a GPU."""
+    from .engine import Engine, FP32
+    w = WORKLOADS[name]
+    n, T = w["n"], w["T"]
+    rng = np.random.default_rng(seed)
+    side = np.sqrt(n) * 250.0
+    px, py = rng.uniform(0, side, n), rng.uniform(0, side, n)
+    area = np.random.default_rng(seed + 1).lognormal(0.0, 0.5, n)
+    alpha, b, e = TRUTH["alpha"], TRUTH["b"], TRUTH["e"]
+    eng = Engine(n, 2, 1, precision=FP32, device=device)
+    eng.set_landscape_coords(px, py, area)
+    eng.set_source_units(None)
+    eng.set_params([dict(e=e, c=1.0, alpha=alpha, b=b)])
+    z = np.zeros((T, n), dtype=np.uint8)
+    z[0] = rng.random(n) < 0.5
+    c = None
+    for t in range(T - 1):
+        y = z[t] & (rng.random(n) > e)
+        eng.set_state(np.stack([z[t], z[t]])[None], y[None, None])
+        S = eng.connectivity()[0, 0]
+        if c is None:
+            c = float(TRUTH["target_mean_C"] / max(S.mean(), 1e-30))
+        z[t + 1] = np.where(y == 1, 1, rng.random(n) < np.minimum(1.0, c * S))
+    eng.close()
+    obs = z.astype(np.int8)
+    hide = rng.random(z.shape) < 0.05
+    hide[0] = False
+    obs[hide] = -1
+    truth = dict(e=e, c=c, alpha=alpha, b=b, p=1.0)
+    return dict(name=name, n=n, T=T, px=px, py=py, area=area, obs=obs, z_true=z, truth=truth, detect=0,
+                chains_per_gpu=w["chains_per_gpu"], desc=w["desc"])
+
+
 def make_workload(name: str, seed: int = 12345):
     w = WORKLOADS[name]
     n, T = w["n"], w["T"]
+    if n > 20000:
+        return make_workload_large(name, seed)
     rng = np.random.default_rng(seed)
     side = np.sqrt(n) * 250.0
     px, py = rng.uniform(0, side, n), rng.uniform(0, side, n)

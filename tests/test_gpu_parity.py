@@ -291,6 +291,55 @@ def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T, variant):
     rel_close(S32[same], S64[same], 1e-5, floor=1e-9)
 
 
+def test_fast_sweep_variants_agree(monkeypatch):
+    """The launch geometry of the fast sweep (threads per task, cluster size, in-CTA pre-reduction for
+    the large-N variants) must not change what a chain does: the Philox thresholds are keyed by cell,
+    so different geometries agree except where a log-odds ties with its threshold in FP32."""
+    rng = np.random.default_rng(4242)
+    n, T, C = 9000, 5, 3
+    spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.5, miss=0.03)
+    par = pdict(e=0.35, c=0.004, alpha=1 / 400, b=0.5)
+    sc = mb.engine.sampler_config(sample_e=0, sample_c=0, update_z=0, n_adapt=0)
+    outs = {}
+    for tpt, cs in ((512, 4), (1024, 8), (2048, 8), (8192, 8), (512, 1)):
+        monkeypatch.setenv("MP_FAST_TPT", str(tpt)); monkeypatch.setenv("MP_FAST_CS", str(cs))
+        with make_engine(spec, n_chains=C, precision=mb.FP32, seed=5, max_draws=1) as eng:
+            eng.set_params([par] * C)
+            eng.set_state(np.stack([z] * C), np.stack([y] * C))
+            eng.set_sampler(sc)
+            eng.connectivity(fetch=False)
+            eng.sweep(1)
+            outs[(tpt, cs)] = (eng.get_state()[1], eng.get_connectivity(), eng.connectivity())
+    ref_y, ref_S, _ = outs[(512, 4)]
+    cand = ((z[:-1] & z[1:]) == 1).sum() * C
+    for key, (yy, S_inc, S_new) in outs.items():
+        assert (yy != ref_y).sum() <= max(2, 5e-4 * cand), key
+        rel_close(S_inc, S_new, 1e-6, floor=1e-9)
+        assert ((yy <= z[None, :-1]) & (yy <= z[None, 1:])).all()
+
+
+def test_large_landscape_sweep_is_consistent():
+    """N = 40,000 patches (beyond one CTA's shared memory: cluster of 8 x 256 threads, in-CTA
+    pre-reduction): after a sweep the incrementally updated S equals a fresh recomputation and the
+    state stays feasible."""
+    rng = np.random.default_rng(99)
+    n, T = 40000, 3
+    spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.45, miss=0.02, areas=False)
+    par = pdict(e=0.3, c=0.004, alpha=1 / 400)
+    with make_engine(spec, n_chains=1, precision=mb.FP32, seed=8, max_draws=2) as eng:
+        eng.set_params([par])
+        eng.set_state(z[None], y[None])
+        eng.set_sampler(mb.engine.sampler_config(n_adapt=0))
+        eng.connectivity(fetch=False)
+        eng.sweep(2)
+        zz, yy = eng.get_state()
+        S_inc = eng.get_connectivity(); S_new = eng.connectivity()
+        d = eng.get_draws()
+    rel_close(S_inc, S_new, 1e-6, floor=1e-9)
+    assert ((yy[0] <= zz[0][:-1]) & (yy[0] <= zz[0][1:])).all()
+    assert np.isfinite(d[:, :, 5]).all() and (yy != y[None]).sum() > 1000
+
+
 def test_chain_offset_selects_the_stream():
     """A chain's random stream depends on its GLOBAL id only: chains [2,3] run alone reproduce
     chains 2,3 of a 4-chain engine (the property MIDASPOM_MPI's row split relies on, :361-372)."""
