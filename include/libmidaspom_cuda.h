@@ -78,7 +78,7 @@ typedef struct {
 /* kernel categories for mp_get_timing */
 enum { MP_K_CONN = 0, MP_K_COL = 1, MP_K_SWEEP_Y = 2, MP_K_SWEEP_Z = 3, MP_K_SMALL = 4, MP_K_SIM = 5, MP_K_NCAT = 6 };
 /* device buffers for mp_device_ptr (zero-copy hand-off to NCCL / torch) */
-enum { MP_BUF_DRAWS = 0, MP_BUF_Z = 1, MP_BUF_Y = 2, MP_BUF_S = 3, MP_BUF_PARAMS = 4 };
+enum { MP_BUF_DRAWS = 0, MP_BUF_Z = 1, MP_BUF_Y = 2, MP_BUF_S = 3, MP_BUF_PARAMS = 4, MP_BUF_S_PROP = 5 };
 
 const char *mp_version(void);
 int mp_device_count(void);
@@ -121,6 +121,15 @@ int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse);
 int mp_set_sampler(mp_engine *h, const mp_sampler_config *sc);
 int mp_sweep(mp_engine *h, int nsweeps);            /* asynchronous on the engine stream */
 int mp_synchronize(mp_engine *h);
+/* One chain sharded over several GPUs (large N): every rank holds a full replica and runs the four phases of
+ * a sweep with a collective in between (midaspom_b200/distributed.py: ShardedChain).
+ *   mp_set_shard: this engine evaluates the connectivity of target patches [conn_lo, conn_hi) only (conn_hi < 0:
+ *     all) and scans the (chain, year) tasks task_first, task_first + task_stride, ... only.
+ *   mp_sweep_phase: 0 proposal + connectivity (sum S / S_prop over ranks afterwards; flags_out bit 0: resident S
+ *     recomputed, bit 1: proposal computed), 1 Metropolis decisions + z update, 2 y scan of the owned tasks
+ *     (exchange the owned rows of y and S afterwards), 3 e/p update + record.  mp_sweep == the four phases. */
+int mp_set_shard(mp_engine *h, int conn_lo, int conn_hi, int task_first, int task_stride);
+int mp_sweep_phase(mp_engine *h, int phase, int *flags_out);
 int mp_num_draws(mp_engine *h);
 int mp_get_draws(mp_engine *h, int first, int count, double *out /* count*C*MP_NDRAW */);
 int mp_reset_draws(mp_engine *h);

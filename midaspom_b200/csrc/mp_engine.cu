@@ -46,7 +46,9 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     a.aw[0] = (const R *)h->d_aw[0]; a.aw[1] = (const R *)h->d_aw[1];
     a.S[0] = h->d_S[0]; a.S[1] = h->d_S[1];
     a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords; a.set_base = set_base;
-    dim3 grid((h->cfg.n_patches + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
+    a.k_lo = h->conn_lo; a.k_hi = h->conn_hi < 0 ? h->cfg.n_patches : h->conn_hi;
+    if (a.k_hi <= a.k_lo) return MP_OK;
+    dim3 grid((a.k_hi - a.k_lo + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
     const int ny = a.ntrans;
     if (ny <= 8) k_conn<R, GEOM, 8><<<grid, CONN_TILE, 0, h->stream>>>(a);
     else if (ny <= 16) k_conn<R, GEOM, 16><<<grid, CONN_TILE, 0, h->stream>>>(a);
@@ -125,9 +127,12 @@ static int launch_sweep_y_fast(mp_engine *h)
     const int n = h->cfg.n_patches, ntrans = h->cfg.n_years - 1, C = h->cfg.n_chains;
     {
         Timed tm(h, MP_K_SMALL);
-        k_build_candidates<<<C * ntrans, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
-                                                                (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
-                                                                h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS);
+        const int ntask = (C * ntrans - h->task_first + h->task_stride - 1) / h->task_stride;
+        if (ntask <= 0) return MP_OK;
+        k_build_candidates<<<ntask, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
+                                                           (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
+                                                           h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS,
+                                                           h->task_first, h->task_stride);
         CK(cudaGetLastError());
     }
     Timed tm(h, MP_K_SWEEP_Y);
@@ -144,6 +149,7 @@ static int launch_sweep_y_fast(mp_engine *h)
 template <typename R> static int launch_sweep_y(mp_engine *h)
 {
     if (fast_sweep_ok(h)) return launch_sweep_y_fast(h);
+    REQUIRE(h->task_first == 0 && h->task_stride == 1, MP_ERR_UNSUPPORTED, "year sharding needs the FP32 fast sweep");
     const size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
     REQUIRE(smem <= 227 * 1024, MP_ERR_UNSUPPORTED, "n_patches too large for the shared-memory resident y sweep");
     switch (h->geom) {
@@ -186,15 +192,21 @@ template <typename R> static int loglik_resident(mp_engine *h, double *d_draw_ro
     return MP_OK;
 }
 
-// one MCMC iteration of every resident chain
-template <typename R> static int sweep_once(mp_engine *h)
+// One MCMC iteration of every resident chain, in four phases.  A single engine runs them back to back
+// (sweep_once); a chain sharded over several GPUs (distributed.ShardedChain) runs the same phases with a
+// collective between them: each rank evaluates its own target patches in phase 0 and its own years in
+// phase 2, everything else is replicated and deterministic, so all ranks take identical decisions.
+enum { PH_PROPOSE_CONN = 0, PH_DECIDE_Z = 1, PH_SWEEP_Y = 2, PH_FINISH = 3 };
+
+// phase 0: proposal for (alpha, b), connectivity of the proposal (and the periodic refresh of the resident S)
+// on the target range [conn_lo, conn_hi).  Returns bit 0 = resident S recomputed, bit 1 = proposal computed.
+template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out)
 {
     int rc;
     const int C = h->cfg.n_chains;
     const SamplerDev sd = sampler_dev(h);
     const bool do_ab = h->sc.sample_alpha || h->sc.sample_b;
-    const long long cells = (long long)ycells(h);
-    // A: refresh S, joint Metropolis step on (log alpha, b)
+    const bool sharded = h->conn_hi >= 0;
     if ((rc = launch_pack_y(h)) != MP_OK) return rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
     if (do_ab) {
@@ -206,8 +218,23 @@ template <typename R> static int sweep_once(mp_engine *h)
     // The resident S is maintained by exact rank-1 updates; the FP32 engine recomputes it from scratch only
     // every MP_REFRESH_EVERY sweeps (the FP64 parity engine every sweep, like the CPU twin).
     const bool refresh = is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0 || !h->S_valid;
+    if (sharded) {   // other ranks fill the other target columns: start from zeros so that a sum over ranks assembles S
+        if (refresh) CK(cudaMemsetAsync(h->d_S[0], 0, nC(h) * ycells(h) * 8, h->stream));
+        if (do_ab) CK(cudaMemsetAsync(h->d_S[1], 0, nC(h) * ycells(h) * 8, h->stream));
+    }
     if ((rc = launch_conn<R>(h, refresh ? 0 : 1, (refresh ? 1 : 0) + (do_ab ? 1 : 0))) != MP_OK) return rc;
     h->S_valid = true;
+    if (flags_out) *flags_out = (refresh ? 1 : 0) | (do_ab ? 2 : 0);
+    return MP_OK;
+}
+// phase 1: Metropolis decisions on (alpha, b) and c, Gibbs update of the latent z cells
+template <typename R> static int phase_decide_z(mp_engine *h)
+{
+    int rc;
+    const int C = h->cfg.n_chains;
+    const SamplerDev sd = sampler_dev(h);
+    const bool do_ab = h->sc.sample_alpha || h->sc.sample_b;
+    const long long cells = (long long)ycells(h);
     if ((rc = launch_col<R>(h, do_ab ? 2 : 1, h->d_par, h->d_S[0], h->d_prop, h->d_S[1])) != MP_OK) return rc;
     { Timed tm(h, MP_K_SMALL);
       k_decide_ab<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
@@ -220,7 +247,6 @@ template <typename R> static int sweep_once(mp_engine *h)
                                                     cells, h->cfg.n_patches);
         CK(cudaGetLastError());
     }
-    // B: Metropolis steps on c (S unchanged)
     if (h->sc.sample_c)
         for (int s = 0; s < h->sc.n_c_steps; s++) {
             { Timed tm(h, MP_K_SMALL);
@@ -233,15 +259,25 @@ template <typename R> static int sweep_once(mp_engine *h)
                                                 h->d_partial[0], h->nblk_col, h->d_llc);
             CK(cudaGetLastError());
         }
-    // D: latent occupancy cells ; E: intermediate states
     if (h->sc.update_z) if ((rc = launch_update_z<R>(h)) != MP_OK) return rc;
-    if (h->sc.update_y) if ((rc = launch_sweep_y<R>(h)) != MP_OK) return rc;
-    // C, F: e and p from the sufficient counts
+    return MP_OK;
+}
+// phase 2: Gibbs scan of the intermediate states of the (chain, year) tasks owned by this engine
+template <typename R> static int phase_sweep_y(mp_engine *h)
+{
+    if (h->sc.update_y) return launch_sweep_y<R>(h);
+    return MP_OK;
+}
+// phase 3: e and p from the sufficient counts, record the draw
+template <typename R> static int phase_finish(mp_engine *h)
+{
+    int rc;
+    const int C = h->cfg.n_chains;
+    const SamplerDev sd = sampler_dev(h);
     if ((rc = launch_counts(h)) != MP_OK) return rc;
     { Timed tm(h, MP_K_SMALL);
       k_update_ep<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_lsig, h->d_counts, C);
       CK(cudaGetLastError()); }
-    // record
     if ((rc = launch_col<R>(h, 1, h->d_par, h->d_S[0], h->d_par, h->d_S[0])) != MP_OK) return rc;
     {
         Timed tm(h, MP_K_SMALL);
@@ -252,6 +288,14 @@ template <typename R> static int sweep_once(mp_engine *h)
     }
     h->sweep++;
     return MP_OK;
+}
+template <typename R> static int sweep_once(mp_engine *h)
+{
+    int rc;
+    if ((rc = phase_propose_conn<R>(h, nullptr)) != MP_OK) return rc;
+    if ((rc = phase_decide_z<R>(h)) != MP_OK) return rc;
+    if ((rc = phase_sweep_y<R>(h)) != MP_OK) return rc;
+    return phase_finish<R>(h);
 }
 
 // ------------------------------------------------------------------ C ABI
@@ -683,6 +727,31 @@ int mp_sweep(mp_engine *h, int nsweeps)
     }
     return MP_OK;
 }
+int mp_set_shard(mp_engine *h, int conn_lo, int conn_hi, int task_first, int task_stride)
+{
+    if (!h) return MP_ERR_ARG;
+    const int ntask = h->cfg.n_chains * (h->cfg.n_years - 1);
+    REQUIRE(task_stride >= 1 && task_first >= 0 && task_first < std::max(ntask, 1) + task_stride, MP_ERR_ARG, "mp_set_shard: bad task subset");
+    REQUIRE(conn_hi < 0 || (conn_lo >= 0 && conn_lo <= conn_hi && conn_hi <= h->cfg.n_patches), MP_ERR_ARG, "mp_set_shard: bad patch range");
+    h->conn_lo = conn_hi < 0 ? 0 : conn_lo; h->conn_hi = conn_hi; h->task_first = task_first; h->task_stride = task_stride;
+    return MP_OK;
+}
+int mp_sweep_phase(mp_engine *h, int phase, int *flags_out)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = check_ready(h);
+    if (rc != MP_OK) return rc;
+    REQUIRE(h->have_sc && h->have_obs, MP_ERR_STATE, "sampler not configured (mp_init_chains / mp_set_sampler)");
+    REQUIRE(!is64(h) || (h->conn_hi < 0 && h->task_stride == 1), MP_ERR_UNSUPPORTED, "sharded phases need the FP32 engine");
+    switch (phase) {
+    case PH_PROPOSE_CONN: return is64(h) ? phase_propose_conn<double>(h, flags_out) : phase_propose_conn<float>(h, flags_out);
+    case PH_DECIDE_Z: return is64(h) ? phase_decide_z<double>(h) : phase_decide_z<float>(h);
+    case PH_SWEEP_Y: return is64(h) ? phase_sweep_y<double>(h) : phase_sweep_y<float>(h);
+    case PH_FINISH: return is64(h) ? phase_finish<double>(h) : phase_finish<float>(h);
+    default: h->err = "mp_sweep_phase: unknown phase"; return MP_ERR_ARG;
+    }
+}
 int mp_synchronize(mp_engine *h)
 {
     if (!h) return MP_ERR_ARG;
@@ -776,6 +845,7 @@ int mp_device_ptr(mp_engine *h, int which, void **ptr, size_t *bytes)
     case MP_BUF_Z: p = h->d_z; b = nC(h) * zcells(h); break;
     case MP_BUF_Y: p = h->d_y; b = nC(h) * ycells(h); break;
     case MP_BUF_S: p = h->d_S[0]; b = nC(h) * ycells(h) * 8; break;
+    case MP_BUF_S_PROP: p = h->d_S[1]; b = nC(h) * ycells(h) * 8; break;
     case MP_BUF_PARAMS: p = h->d_par; b = nC(h) * sizeof(mp_params); break;
     default: h->err = "mp_device_ptr: unknown buffer"; return MP_ERR_ARG;
     }

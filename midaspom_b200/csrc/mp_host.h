@@ -51,6 +51,8 @@ struct mp_engine {
     int sm_count = 148;
     int refresh_every = 16;          // FP32 engine: sweeps between from-scratch recomputations of the resident S
     bool S_valid = false;            // resident S corresponds to the resident (y, alpha, b)
+    int task_first = 0, task_stride = 1;   // (chain, year) tasks of the y sweep run by this engine (year sharding)
+    int conn_lo = 0, conn_hi = -1;        // target patches of k_conn run by this engine (patch sharding); hi < 0 = all
     int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides
     int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
     // timing

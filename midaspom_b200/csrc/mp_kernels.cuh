@@ -62,6 +62,7 @@ template <typename R> struct ConnArgs {
     const uint32_t *ybits;
     int ntrans, nwords;
     int set_base;          // first parameter set of this launch (blockIdx.z counts from it)
+    int k_lo, k_hi;        // target patches [k_lo, k_hi) of this launch (patch sharding over GPUs; whole range otherwise)
 };
 
 template <typename R, int GEOM, int NYB>
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
     __shared__ uint32_t sbits[CONN_TILE];
     __shared__ __align__(16) double sy01[CONN_TILE][NYB];
     const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z + a.set_base, tid = threadIdx.x;
-    const int kbase = blockIdx.x * CONN_TILE * CONN_TGT + tid;
+    const int kbase = a.k_lo + blockIdx.x * CONN_TILE * CONN_TGT + tid;
     const mp_params *parp = set ? a.par[1] : a.par[0];
     const R apre = alpha_pre<R>(parp[c].alpha);
     const R *aw = (set ? a.aw[1] : a.aw[0]) + (size_t)c * n;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
     for (int g = 0; g < CONN_TGT; g++) {
         const int k = kbase + g * CONN_TILE;
         tx[g] = 0; ty[g] = 0;
-        if (GEOM == MP_GEOM_COORDS && k < n) { tx[g] = a.ls.px[k]; ty[g] = a.ls.py[k]; }
+        if (GEOM == MP_GEOM_COORDS && k < a.k_hi) { tx[g] = a.ls.px[k]; ty[g] = a.ls.py[k]; }
     }
     for (int w = 0; w < a.nwords; w++) {
         const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
 #pragma unroll
             for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
             __syncthreads();
-            if (kbase < n) {
+            if (kbase < a.k_hi) {
                 for (int j = 0; j < CONN_TILE; j++) {
                     if (sbits[j] == 0) continue;                       // tile-uniform: source empty in every year
                     double wd[CONN_TGT];
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
 #pragma unroll
         for (int g = 0; g < CONN_TGT; g++) {
             const int k = kbase + g * CONN_TILE;
-            if (k < n) {
+            if (k < a.k_hi) {
 #pragma unroll
                 for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = acc[g][t];
             }

@@ -81,11 +81,11 @@ __device__ __forceinline__ float warp_sum_f(float v)
 static __global__ void __launch_bounds__(1024)
 k_build_candidates(uint64_t seed, int chain_offset, uint32_t sweep, Landscape<float> ls, const float *__restrict__ aw,
                    const uint8_t *__restrict__ z, const uint8_t *__restrict__ y, CandRec *__restrict__ rec,
-                   int *__restrict__ count /* [task][2]: candidates, occupied */, int T, int coords)
+                   int *__restrict__ count /* [task][2]: candidates, occupied */, int T, int coords, int task_first, int task_stride)
 {
     __shared__ int s_cnt[1024], s_occ[32];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x;
-    const int task = blockIdx.x, c = task / ntrans, t = task - c * ntrans;
+    const int task = task_first + blockIdx.x * task_stride, c = task / ntrans, t = task - c * ntrans;
     const uint8_t *zt = z + ((size_t)c * T + t) * n, *zn = zt + n, *yt = y + ((size_t)c * ntrans + t) * n;
     const int per = (n + 1023) / 1024, q0 = min(n, tid * per), q1 = min(n, q0 + per);
     int cnt = 0, occ = 0;
@@ -141,7 +141,7 @@ template <int GEOM, int CS, int U, int TPT>
 __global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uint8_t *__restrict__ era,
                const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
-               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept)
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, int task_first, int task_stride)
 {
     constexpr int NT = TPT / CS, NW = NT / 32;
     constexpr bool HIER = TPT / 32 > 32;                // more than 32 warps per task: reduce inside the CTA first
@@ -152,7 +152,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
-    const int task = blockIdx.x / CS;
+    const int task = task_first + (blockIdx.x / CS) * task_stride;      // year sharding over GPUs: every task_stride-th task
     const int c = task / ntrans, t = task - c * ntrans;
     float4 *sT = reinterpret_cast<float4 *>(smem_raw);               // {S_hi, S_lo, x, y} of own targets, slot tid + j NT
 
@@ -375,7 +375,10 @@ template <int CS, int U, int TPT> static int launch_fast(mp_engine *h, int ept)
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(h->cfg.n_chains * (h->cfg.n_years - 1) * CS));
+    const int ntask_all = h->cfg.n_chains * (h->cfg.n_years - 1);
+    const int ntask = (ntask_all - h->task_first + h->task_stride - 1) / h->task_stride;
+    if (ntask <= 0) return MP_OK;
+    cfg.gridDim = dim3((unsigned)(ntask * CS));
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
@@ -385,7 +388,7 @@ template <int CS, int U, int TPT> static int launch_fast(mp_engine *h, int ept)
     cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const mp_params *)h->d_par,
                           (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
-                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept));
+                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, h->task_first, h->task_stride));
     return MP_OK;
 }
 template <int CS, int TPT> static int launch_fast_u(mp_engine *h, int ept)

@@ -78,3 +78,112 @@ def posterior_summary(all_draws: np.ndarray, fields=("e", "c", "alpha", "b", "p"
         out[f] = dict(mean=float(x.mean()), sd=float(x.std()), rhat=split_rhat(x),
                       ess=float(sum(ess_geyer(x[:, c]) for c in range(x.shape[1]))))
     return out
+
+
+# ----------------------------------------------------------------------------- one chain over several GPUs
+PH_PROPOSE_CONN, PH_DECIDE_Z, PH_SWEEP_Y, PH_FINISH = 0, 1, 2, 3
+BUF_Y, BUF_S, BUF_S_PROP = 2, 3, 5
+
+
+class _DeviceView:
+    """__cuda_array_interface__ over a buffer owned by an mp_engine (zero-copy torch view)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def engine_tensor(eng, which, shape, typestr, device):
+    import torch
+    ptr, _ = eng.device_ptr(which)
+    return torch.as_tensor(_DeviceView(ptr, shape, typestr), device=device)
+
+
+class ShardedChain:
+    """Large-N runs (BASELINE config 5): every rank holds a full replica of the chain(s); per sweep
+      * the connectivity (N^2 pair terms) is split by TARGET PATCHES: rank r evaluates the columns
+        [lo_r, hi_r) of S / S_prop, an all-reduce(sum) over zero-filled buffers assembles them;
+      * the Gibbs scan of y is split by YEARS: the (chain, year) tasks are independent given z, rank r scans the
+        tasks r, r + W, ...; the updated rows of y (the occupancy state) and S are exchanged the same way;
+      * everything else (Metropolis decisions, z update, counts) is replicated -- identical inputs and identical
+        Philox counters give identical decisions on every rank, so the result equals a single-GPU run bit for bit.
+    `reduce_fn(tensor)` must sum the tensor over ranks in place (torch.distributed.all_reduce by default)."""
+
+    def __init__(self, eng, rank, world, device, reduce_fn=None):
+        import torch
+        self.eng, self.rank, self.world = eng, rank, world
+        C, T, N = eng.C, eng.T, eng.N
+        per = -(-N // world)
+        per = -(-per // 256) * 256                      # whole k_conn CTAs (128 threads x 2 targets)
+        lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+        eng.set_shard(lo, hi, rank, world)
+        self.S = engine_tensor(eng, BUF_S, (C * (T - 1), N), "<f8", device)
+        self.Sp = engine_tensor(eng, BUF_S_PROP, (C * (T - 1), N), "<f8", device)
+        self.y = engine_tensor(eng, BUF_Y, (C * (T - 1), N), "|u1", device)
+        own = (torch.arange(C * (T - 1), device=device) % world) == rank
+        self.not_own = ~own
+        if reduce_fn is None:
+            import torch.distributed as dist
+            reduce_fn = lambda t: dist.all_reduce(t)
+        self.reduce_fn = reduce_fn
+        self.torch = torch
+
+    def phase_a(self):
+        flags = self.eng.sweep_phase(PH_PROPOSE_CONN)
+        self.eng.synchronize()
+        return flags
+
+    def exchange_a(self, flags):
+        if flags & 2:
+            self.reduce_fn(self.Sp)
+        if flags & 1:
+            self.reduce_fn(self.S)
+
+    def phase_b(self):
+        self.eng.sweep_phase(PH_DECIDE_Z)
+        self.eng.sweep_phase(PH_SWEEP_Y)
+        self.eng.synchronize()
+        self.S[self.not_own] = 0
+        self.y[self.not_own] = 0
+
+    def exchange_b(self):
+        self.reduce_fn(self.S)
+        self.reduce_fn(self.y)
+
+    def phase_c(self):
+        self.torch.cuda.synchronize()
+        self.eng.sweep_phase(PH_FINISH)
+
+    def sweep(self, nsweeps=1):
+        for _ in range(nsweeps):
+            flags = self.phase_a()
+            self.exchange_a(flags)
+            self.torch.cuda.synchronize()
+            self.phase_b()
+            self.exchange_b()
+            self.phase_c()
+        self.eng.synchronize()
+
+
+def sweep_emulated_ranks(chains, nsweeps=1):
+    """Run W ShardedChain objects that live in ONE process (one GPU) in lock step, summing their buffers
+    directly instead of through NCCL -- the single-GPU emulation of the multi-rank path used by the tests."""
+    def sum_over(name):
+        tot = sum(getattr(c, name).to(chains[0].torch.float64) for c in chains)
+        for c in chains:
+            getattr(c, name).copy_(tot.to(getattr(c, name).dtype))
+    for _ in range(nsweeps):
+        flags = [c.phase_a() for c in chains]
+        chains[0].torch.cuda.synchronize()
+        if flags[0] & 2:
+            sum_over("Sp")
+        if flags[0] & 1:
+            sum_over("S")
+        chains[0].torch.cuda.synchronize()
+        for c in chains:
+            c.phase_b()
+        chains[0].torch.cuda.synchronize()
+        sum_over("S"); sum_over("y")
+        for c in chains:
+            c.phase_c()
+    for c in chains:
+        c.eng.synchronize()

@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "mp_set_scales", "mp_get_scales", "mp_connectivity", "mp_get_connectivity", "mp_loglik", "mp_loglik_host",
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
-    "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant",
+    "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
 )
 
 
@@ -103,6 +103,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_set_sampler.argtypes = [vp, scp]
     L.mp_sweep.argtypes = [vp, C.c_int]
     L.mp_synchronize.argtypes = [vp]
+    L.mp_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mp_sweep_phase.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     L.mp_num_draws.argtypes = [vp]; L.mp_reset_draws.argtypes = [vp]; L.mp_sweep_index.argtypes = [vp]
     L.mp_get_draws.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mp_simulate.argtypes = [vp, pp, u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, u8p, C.POINTER(C.c_int32)]
@@ -289,6 +291,14 @@ class Engine:
         self._ck(self.lib.mp_sweep(self.h, int(nsweeps)), "mp_sweep")
         if sync:
             self.synchronize()
+
+    def set_shard(self, conn_lo=0, conn_hi=-1, task_first=0, task_stride=1):
+        self._ck(self.lib.mp_set_shard(self.h, conn_lo, conn_hi, task_first, task_stride), "mp_set_shard")
+
+    def sweep_phase(self, phase):
+        flags = C.c_int(0)
+        self._ck(self.lib.mp_sweep_phase(self.h, phase, C.byref(flags)), "mp_sweep_phase")
+        return flags.value
 
     def synchronize(self):
         self._ck(self.lib.mp_synchronize(self.h), "mp_synchronize")

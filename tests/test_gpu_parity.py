@@ -340,6 +340,40 @@ def test_large_landscape_sweep_is_consistent():
     assert np.isfinite(d[:, :, 5]).all() and (yy != y[None]).sum() > 1000
 
 
+def test_sharded_chain_equals_single_engine():
+    """BASELINE config 5 path: one chain sharded over W ranks (connectivity by target patches, y scan by
+    years, replicated decisions) must reproduce the single-engine run bit for bit.  The W ranks are
+    emulated in one process on one GPU, with the NCCL all-reduce replaced by an explicit sum."""
+    import torch
+    from midaspom_b200 import distributed as D
+    rng = np.random.default_rng(31)
+    n, T, C, W = 3000, 7, 2, 3
+    spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.5, miss=0.05)
+    par = pdict(e=0.4, c=0.01, alpha=1 / 400, b=0.5)
+    kw = dict(sample_alpha=1, sample_b=1, c_max=0.2, alpha_min=1e-4, alpha_max=1e-1, n_adapt=4)
+    nsw = 6
+
+    def fresh():
+        eng = make_engine(spec, n_chains=C, precision=mb.FP32, seed=17, max_draws=nsw)
+        eng.set_params([par] * C)
+        eng.init_chains(mb.engine.sampler_config(**kw), disperse=False)
+        return eng
+
+    ref = fresh()
+    ref.sweep(nsw)
+    want = (ref.get_draws(), ref.get_state(), ref.get_connectivity())
+    ref.close()
+    engs = [fresh() for _ in range(W)]
+    chains = [D.ShardedChain(e, r, W, torch.device("cuda", 0), reduce_fn=lambda t: None) for r, e in enumerate(engs)]
+    D.sweep_emulated_ranks(chains, nsw)
+    for e in engs:
+        got = (e.get_draws(), e.get_state(), e.get_connectivity())
+        assert (got[0] == want[0]).all()
+        assert (got[1][0] == want[1][0]).all() and (got[1][1] == want[1][1]).all()
+        assert (got[2] == want[2]).all()
+        e.close()
+
+
 def test_chain_offset_selects_the_stream():
     """A chain's random stream depends on its GLOBAL id only: chains [2,3] run alone reproduce
     chains 2,3 of a 4-chain engine (the property MIDASPOM_MPI's row split relies on, :361-372)."""
