@@ -139,7 +139,11 @@ static int launch_sweep_y_fast(mp_engine *h)
     int tpt = h->fast_tpt ? h->fast_tpt : (n > 6144 ? 512 : 1024);   // threads per task
     if ((n + tpt - 1) / tpt > 31) tpt = 1024;
     for (int big = 2048; (n + tpt - 1) / tpt > 31 && big <= 8192; big *= 2) tpt = big;   // N > 31k: 2048..8192 threads, cluster of 8
-    const int cs = tpt > 1024 ? 8 : (h->fast_cs ? h->fast_cs : pick_cluster(C * ntrans, h->sm_count, 8));
+    // large landscapes: a cluster of 8 holds the task's state; with few tasks per GPU (year sharding) spread each
+    // task over 16 SMs instead -- the scan is latency-bound per flip
+    const int ntask_own = (C * ntrans - h->task_first + h->task_stride - 1) / h->task_stride;
+    const int cs = tpt > 1024 ? (h->fast_cs == 16 || (h->fast_cs == 0 && tpt >= 4096 && ntask_own * 16 <= h->sm_count) ? 16 : 8)
+                              : (h->fast_cs ? h->fast_cs : pick_cluster(C * ntrans, h->sm_count, 8));
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
     case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);

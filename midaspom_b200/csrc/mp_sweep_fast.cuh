@@ -400,10 +400,10 @@ template <int CS, int TPT> static int launch_fast_u(mp_engine *h, int ept)
 static int launch_fast_any(mp_engine *h, int cs, int tpt)
 {
     const int ept = (h->cfg.n_patches + tpt - 1) / tpt;
-    if (tpt > 1024) {                                   // large landscapes: clusters of 8, 256..1024 threads per CTA
+    if (tpt > 1024) {                                   // large landscapes: clusters of 8 (or 16), 256..1024 threads per CTA
         if (tpt == 2048) return launch_fast_u<8, 2048>(h, ept);
-        if (tpt == 4096) return launch_fast_u<8, 4096>(h, ept);
-        return launch_fast_u<8, 8192>(h, ept);
+        if (tpt == 4096) return cs == 16 ? launch_fast_u<16, 4096>(h, ept) : launch_fast_u<8, 4096>(h, ept);
+        return cs == 16 ? launch_fast_u<16, 8192>(h, ept) : launch_fast_u<8, 8192>(h, ept);
     }
     if (tpt == 512) switch (cs) {
         case 1: return launch_fast_u<1, 512>(h, ept);

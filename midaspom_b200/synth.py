@@ -17,6 +17,7 @@ WORKLOADS = {
     "cfg3": dict(n=10000, T=20, chains_per_gpu=8, detect=0, desc="synthetic N=10,000 x T=20, 64 chains over 8 GPUs (8 per GPU)"),
     "tiny": dict(n=256, T=6, chains_per_gpu=4, detect=0, desc="smoke-test size"),
     "cfg5": dict(n=100000, T=30, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=30, one chain"),
+    "cfg5t": dict(n=100000, T=5, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=5, one chain (4 year tasks: what one of 8 GPUs scans in cfg5)"),
     "cfg5s": dict(n=40000, T=12, chains_per_gpu=1, detect=0, desc="synthetic N=40,000 x T=12, one chain (reduced cfg5)"),
 }
 TRUTH = dict(e=0.3, alpha=1.0 / 400.0, b=0.5, p_detect=0.8, target_mean_C=0.3)
