@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
             for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
             __syncthreads();
             if (kbase < a.k_hi) {
+#pragma unroll 2
                 for (int j = 0; j < CONN_TILE; j++) {
                     if (sbits[j] == 0) continue;                       // tile-uniform: source empty in every year
                     double wd[CONN_TGT];
