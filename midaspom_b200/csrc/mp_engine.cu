@@ -239,10 +239,15 @@ template <typename R> static int phase_decide_z(mp_engine *h)
     const SamplerDev sd = sampler_dev(h);
     const bool do_ab = h->sc.sample_alpha || h->sc.sample_b;
     const long long cells = (long long)ycells(h);
+    if (do_ab) {
+        Timed tm(h, MP_K_SMALL);
+        k_ridge_c<<<C, 256, 0, h->stream>>>(sd, h->d_par, h->d_prop, h->d_S[0], h->d_S[1], cells, h->d_flags, h->d_ljac);
+        CK(cudaGetLastError());
+    }
     if ((rc = launch_col<R>(h, do_ab ? 2 : 1, h->d_par, h->d_S[0], h->d_prop, h->d_S[1])) != MP_OK) return rc;
     { Timed tm(h, MP_K_SMALL);
       k_decide_ab<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
-                                           h->d_partial[0], h->d_partial[1], h->nblk_col, h->d_llc, do_ab ? 1 : 0);
+                                           h->d_partial[0], h->d_partial[1], h->nblk_col, h->d_llc, do_ab ? 1 : 0, h->d_ljac);
       CK(cudaGetLastError()); }
     if (do_ab) {
         Timed tm(h, MP_K_SMALL);
@@ -325,7 +330,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_ljac };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -380,7 +385,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_ybits, C * h->nwords * N * 4 }, { (void **)&h->d_S[0], C * (T - 1) * N * 8 },
         { (void **)&h->d_S[1], C * (T - 1) * N * 8 }, { &h->d_aw[0], C * N * R }, { &h->d_aw[1], C * N * R },
         { (void **)&h->d_partial[0], C * MAX_COL_BLOCKS * 8 }, { (void **)&h->d_partial[1], C * MAX_COL_BLOCKS * 8 },
-        { (void **)&h->d_llc, C * 8 }, { (void **)&h->d_logu, C * 8 }, { (void **)&h->d_parts, C * MP_NPART * 8 },
+        { (void **)&h->d_llc, C * 8 }, { (void **)&h->d_logu, C * 8 }, { (void **)&h->d_ljac, C * 8 }, { (void **)&h->d_parts, C * MP_NPART * 8 },
         { (void **)&h->d_scalar, 64 }, { (void **)&h->d_flags, C * 4 * sizeof(int) },
         { (void **)&h->d_counts, C * NCOUNT * sizeof(unsigned long long) },
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },

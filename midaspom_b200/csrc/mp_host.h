@@ -38,6 +38,7 @@ struct mp_engine {
     double *d_S[2] = { nullptr, nullptr };
     void *d_aw[2] = { nullptr, nullptr };
     double *d_partial[2] = { nullptr, nullptr };
+    double *d_ljac = nullptr;        // log Jacobian of the ridge move (alpha, b, c) per chain
     double *d_llc = nullptr, *d_logu = nullptr, *d_parts = nullptr, *d_scalar = nullptr;
     int *d_flags = nullptr;
     unsigned long long *d_counts = nullptr;

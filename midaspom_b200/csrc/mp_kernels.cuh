@@ -266,11 +266,36 @@ __global__ void k_propose_ab(SamplerDev sd, uint32_t sweep, const mp_params *__r
     flags[c * 4 + 1] = 0;
     logu[c] = log(u01(r.z));
 }
+// Ridge move: (alpha, b) mostly rescale S, and c S is what the data pin down.  The proposal carries
+// c' = c mean(S)/mean(S') -- a deterministic, reversible shift of log c (mean S depends on (alpha, b, y)
+// only) -- and the Hastings ratio gains the Jacobian c'/c of the uniform-in-c prior seen in log c.
+// One CTA per chain; fixed-order sums.  ljac[c] = log(c'/c); flags[c*4+0] &= c' within bounds.
+__global__ void __launch_bounds__(256)
+k_ridge_c(SamplerDev sd, const mp_params *__restrict__ par, mp_params *__restrict__ prop, const double *__restrict__ S,
+          const double *__restrict__ S2, long long cells, int *__restrict__ flags, double *__restrict__ ljac)
+{
+    __shared__ double scratch[32];
+    const int c = blockIdx.x;
+    double m1 = 0.0, m2 = 0.0;
+    for (long long i = threadIdx.x; i < cells; i += blockDim.x) { m1 += S[(size_t)c * cells + i]; m2 += S2[(size_t)c * cells + i]; }
+    m1 = block_sum(m1, scratch);
+    __syncthreads();
+    m2 = block_sum(m2, scratch);
+    if (threadIdx.x != 0) return;
+    double lj = 0.0;
+    if (sd.sc.sample_c && m1 > 0.0 && m2 > 0.0) {
+        const double c2 = par[c].c * (m1 / m2);
+        lj = log(c2 / par[c].c);
+        prop[c].c = c2;
+        if (!(c2 >= sd.sc.c_min && c2 <= sd.sc.c_max)) flags[c * 4 + 0] = 0;
+    }
+    ljac[c] = lj;
+}
 // llc[c] receives the colonisation log-likelihood of the state kept
 __global__ void k_decide_ab(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
                             double *__restrict__ lsig, int *__restrict__ flags, const double *__restrict__ logu,
                             const double *__restrict__ part_cur, const double *__restrict__ part_prop, int nblk,
-                            double *__restrict__ llc, int do_mh)
+                            double *__restrict__ llc, int do_mh, const double *__restrict__ ljac)
 {
     const int c = blockIdx.x;
     const double cur = reduce_partials(part_cur + (size_t)c * nblk, nblk);
@@ -280,7 +305,7 @@ __global__ void k_decide_ab(SamplerDev sd, uint32_t sweep, mp_params *__restrict
     int acc = 0;
     double keep = cur;
     if (do_mh) {
-        const double d = pr - cur;
+        const double d = pr - cur + ljac[c];
         if (flags[c * 4 + 0] && !isnan(d) && logu[c] < d) { acc = 1; keep = pr; par[c] = prop[c]; }
         flags[c * 4 + 1] = acc;
         if (sweep < (uint32_t)sd.sc.n_adapt) {

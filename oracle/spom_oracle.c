@@ -490,8 +490,20 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
         if (prop.alpha >= cfg->alpha_min && prop.alpha <= cfg->alpha_max && prop.b >= cfg->b_min && prop.b <= cfg->b_max) {
             double *S2 = malloc((cells ? cells : 1) * sizeof(double));
             spom_refresh_S(m, &prop, y, S2);
-            const double llc2 = ll_col_all(m, &prop, z, y, S2);
-            if (mh_accept(logu, llc2 - llc)) { acc = 1; *par = prop; memcpy(S, S2, cells * sizeof(double)); llc = llc2; }
+            /* ridge move: (alpha, b) mostly rescale S, and c S is what the data pin down.  Propose
+             * c' = c mean(S)/mean(S') together with (alpha', b'): a deterministic, reversible shift of log c
+             * (mean S depends on (alpha, b, y) only), so the Hastings ratio only gains the Jacobian c'/c of the
+             * uniform-in-c prior seen in log c. */
+            double ljac = 0.0;
+            if (cfg->sample_c && cells) {
+                double m1 = 0.0, m2 = 0.0;
+                for (size_t i = 0; i < cells; i++) { m1 += S[i]; m2 += S2[i]; }
+                if (m1 > 0.0 && m2 > 0.0) { prop.c = par->c * (m1 / m2); ljac = log(prop.c / par->c); }
+            }
+            if (prop.c >= cfg->c_min && prop.c <= cfg->c_max) {
+                const double llc2 = ll_col_all(m, &prop, z, y, S2);
+                if (mh_accept(logu, llc2 - llc + ljac)) { acc = 1; *par = prop; memcpy(S, S2, cells * sizeof(double)); llc = llc2; }
+            }
             free(S2);
         }
         if (adapting) {
