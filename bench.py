@@ -51,12 +51,13 @@ def sampler_kwargs(wl):
     c0 = wl["truth"]["c"]
     return dict(sample_e=1, sample_c=1, sample_alpha=1, sample_b=1, sample_p=int(wl["detect"]),
                 e_min=0.0, e_max=1.0, c_min=0.0, c_max=20.0 * c0, alpha_min=1e-4, alpha_max=1e-1, b_min=0.0, b_max=2.0,
-                p_min=0.0, p_max=1.0, n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1)
+                p_min=0.0, p_max=1.0, n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1,
+                sample_K=int("era" in wl), K_min=0.1, K_max=100.0, n_v_steps=2)      # die-off variant: K on the reference's range (dieoff.c:113-114)
 
 
 def start_params(wl):
     t = wl["truth"]
-    return dict(e=0.5, c=t["c"], alpha=t["alpha"], b=t["b"], p=t["p"], K=1.0, Ksrc=0.0, dsrc=0.0)
+    return dict(e=0.5 if "era" not in wl else t["e"], c=t["c"], alpha=t["alpha"], b=t["b"], p=t["p"], K=t.get("K", 1.0), Ksrc=0.0, dsrc=0.0)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -106,7 +107,7 @@ def cpu_sample(wl, chains, budget_s, steps=1, warmup=0):
     the y scan on `limit` candidate cells per year, extrapolated to all candidates."""
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib as O
-    m = O.Model(wl["obs"], geom=O.GEOM_COORDS, px=wl["px"], py=wl["py"], area=wl["area"], detect=wl["detect"])
+    m = O.Model(wl["obs"], geom=O.GEOM_COORDS, px=wl["px"], py=wl["py"], area=wl["area"], detect=wl["detect"], era=wl.get("era"))
     cfg = O.sampler_cfg(**sampler_kwargs(wl))
     sp = start_params(wl)
     cores = O.lib().spom_max_threads()
@@ -184,6 +185,7 @@ def run_ours(args, rank, local_rank, world):
     obs_pinned = torch.from_numpy(wl["obs"].copy()).pin_memory()
     obs_host = obs_pinned.numpy()
     eng.set_observations(obs_host)
+    eng.set_era(wl.get("era"))
     eng.set_params([start_params(wl)] * cpg)
     eng.init_chains(mb.engine.sampler_config(**sampler_kwargs(wl)), disperse=False)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
@@ -281,7 +283,7 @@ def run_ours(args, rank, local_rank, world):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"{args.workload}: {wl['desc']}", n_patches=n, n_years=T, chains=chains_total,
                                 chains_per_gpu=cpg, geometry="planar coordinates + areas, on-the-fly weights",
-                                sampled=["e", "c", "alpha", "b"] + (["p"] if wl["detect"] else []),
+                                sampled=["e", "c", "alpha", "b"] + (["p"] if wl["detect"] else []) + (["K"] if "era" in wl else []),
                                 l2="flushed between timed steps (256 MiB write)", parallelism=f"chains x{world}"),
                     clocks=clk.summary(),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(obs_host.nbytes),

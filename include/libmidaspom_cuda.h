@@ -43,8 +43,8 @@ enum { MP_OK = 0, MP_ERR_ARG = -1, MP_ERR_CUDA = -2, MP_ERR_STATE = -3, MP_ERR_U
 enum { MP_FP32 = 0, MP_FP64 = 1 };                       /* arithmetic of the weight / log terms */
 enum { MP_GEOM_LINEAR = 0, MP_GEOM_COORDS = 1, MP_GEOM_DENSE = 2 };
 
-#define MP_NDRAW 8   /* per (sweep, chain): e, c, alpha, b, p, loglik, #y=1, #z=1 */
-#define MP_NLSIG 5   /* log proposal scales: e, c, alpha, b, p */
+#define MP_NDRAW 11  /* per (sweep, chain): e, c, alpha, b, p, loglik, #y=1, #z=1, K, Ksrc, dsrc */
+#define MP_NLSIG 8   /* log proposal scales: e, c, alpha, b, p, K, Ksrc, dsrc */
 #define MP_NPART 4   /* loglik parts: extinction, colonisation, year-0 prior, detection */
 
 typedef struct mp_engine mp_engine;
@@ -69,10 +69,13 @@ typedef struct { double e, c, alpha, b, p, K, Ksrc, dsrc; } mp_params;
 
 typedef struct {
     double  e_min, e_max, c_min, c_max, alpha_min, alpha_max, b_min, b_max, p_min, p_max;
+    double  K_min, K_max, Ksrc_min, Ksrc_max, dsrc_min, dsrc_max;   /* variant parameters (dieoff.c:283-286, loss.c:319-322 grids) */
     int32_t sample_e, sample_c, sample_alpha, sample_b, sample_p;
     int32_t n_e_steps, n_c_steps;   /* Metropolis sub-steps per sweep */
     int32_t n_adapt;                /* sweeps during which proposal scales adapt */
     int32_t update_z, update_y;     /* Gibbs updates of latent occupancy / intermediate state */
+    int32_t sample_K, sample_Ksrc, sample_dsrc;   /* Metropolis on the pre-event scaling / external source (log-uniform K, Ksrc; uniform dsrc) */
+    int32_t n_v_steps;              /* sub-steps per sweep for each sampled variant parameter */
 } mp_sampler_config;
 
 /* kernel categories for mp_get_timing */

@@ -268,6 +268,24 @@ template <typename R> static int phase_decide_z(mp_engine *h)
                                                 h->d_partial[0], h->nblk_col, h->d_llc);
             CK(cudaGetLastError());
         }
+    // V: variant parameters (K, Ksrc, dsrc): extinction part from the counts, colonisation part over the cells
+    if (h->sc.sample_K || h->sc.sample_Ksrc || h->sc.sample_dsrc) {
+        if ((rc = launch_counts(h)) != MP_OK) return rc;
+        for (int which = 0; which < 3; which++) {
+            const int on = which == 0 ? h->sc.sample_K : which == 1 ? h->sc.sample_Ksrc : h->sc.sample_dsrc;
+            if (!on) continue;
+            for (int s = 0; s < h->sc.n_v_steps; s++) {
+                { Timed tm(h, MP_K_SMALL);
+                  k_propose_var<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, which, s, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
+                  CK(cudaGetLastError()); }
+                if ((rc = launch_col<R>(h, 1, h->d_prop, h->d_S[0], h->d_prop, h->d_S[0])) != MP_OK) return rc;
+                Timed tm(h, MP_K_SMALL);
+                k_decide_var<<<C, 32, 0, h->stream>>>(sd, h->sweep, which, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
+                                                      h->d_partial[0], h->nblk_col, h->d_llc, h->d_counts);
+                CK(cudaGetLastError());
+            }
+        }
+    }
     if (h->sc.update_z) if ((rc = launch_update_z<R>(h)) != MP_OK) return rc;
     return MP_OK;
 }
@@ -641,7 +659,9 @@ int mp_flip_delta(mp_engine *h, int chain, int t, int k, double *dll)
 int mp_set_sampler(mp_engine *h, const mp_sampler_config *sc)
 {
     if (!h || !sc) return MP_ERR_ARG;
-    REQUIRE(sc->n_e_steps >= 0 && sc->n_c_steps >= 0, MP_ERR_ARG, "negative sub-step count");
+    REQUIRE(sc->n_e_steps >= 0 && sc->n_c_steps >= 0 && sc->n_v_steps >= 0, MP_ERR_ARG, "negative sub-step count");
+    REQUIRE(!sc->sample_K || (sc->K_min > 0 && sc->K_max >= sc->K_min), MP_ERR_ARG, "sample_K needs 0 < K_min <= K_max");
+    REQUIRE(!sc->sample_Ksrc || (sc->Ksrc_min > 0 && sc->Ksrc_max >= sc->Ksrc_min), MP_ERR_ARG, "sample_Ksrc needs 0 < Ksrc_min <= Ksrc_max");
     h->sc = *sc; h->have_sc = true;
     return MP_OK;
 }
@@ -670,9 +690,13 @@ int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
             if (sc->sample_b) p.b = sc->b_min + u01(r.w) * (sc->b_max - sc->b_min);
             r = rng(h->cfg.seed, gc, 0, RK_INIT_PARAM, 1, 0);
             if (sc->sample_p) p.p = sc->p_min + u01(r.x) * (sc->p_max - sc->p_min);
+            if (sc->sample_K) p.K = sc->K_min * pow(sc->K_max / sc->K_min, u01(r.y));
+            if (sc->sample_Ksrc) p.Ksrc = sc->Ksrc_min * pow(sc->Ksrc_max / sc->Ksrc_min, u01(r.z));
+            if (sc->sample_dsrc) p.dsrc = sc->dsrc_min + u01(r.w) * (sc->dsrc_max - sc->dsrc_min);
         }
         double *ls = &lsig[c * MP_NLSIG];
         ls[0] = log(0.05); ls[1] = log(0.1 * p.c); ls[2] = log(0.05); ls[3] = log(0.05); ls[4] = log(0.05);
+        ls[5] = log(0.1); ls[6] = log(0.1); ls[7] = log(0.1 * (sc->dsrc_max > sc->dsrc_min ? sc->dsrc_max - sc->dsrc_min : 1.0));
         uint8_t *zc = &z[c * T * N], *yc = &y[c * (T - 1) * N];
         for (size_t t = 0; t < T; t++)
             for (size_t k = 0; k < N; k++) {

@@ -355,6 +355,39 @@ __global__ void k_decide_c(SamplerDev sd, uint32_t sweep, mp_params *__restrict_
     if (flags[c * 4 + 0] && !isnan(d) && logu[c] < d) { acc = 1; par[c] = prop[c]; llc[c] = pr; }
     if (sweep < (uint32_t)sd.sc.n_adapt) lsig[c * MP_NLSIG + 1] += adapt_gain(sweep) * (acc - 0.44);
 }
+// variant parameters: which = 0 K (log random walk), 1 Ksrc (log random walk), 2 dsrc (additive)
+__global__ void k_propose_var(SamplerDev sd, uint32_t sweep, int which, int step, const mp_params *__restrict__ par,
+                              mp_params *__restrict__ prop, const double *__restrict__ lsig, int *__restrict__ flags,
+                              double *__restrict__ logu, int nchains)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchains) return;
+    const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_K + (uint32_t)which, (uint32_t)step, 0);
+    double n1, n2;
+    box_muller(r.x, r.y, n1, n2);
+    mp_params q = par[c];
+    int inb;
+    if (which == 0) { q.K = q.K * exp(exp(lsig[c * MP_NLSIG + 5]) * n1); inb = q.K >= sd.sc.K_min && q.K <= sd.sc.K_max; }
+    else if (which == 1) { q.Ksrc = q.Ksrc * exp(exp(lsig[c * MP_NLSIG + 6]) * n1); inb = q.Ksrc >= sd.sc.Ksrc_min && q.Ksrc <= sd.sc.Ksrc_max; }
+    else { q.dsrc = q.dsrc + exp(lsig[c * MP_NLSIG + 7]) * n1; inb = q.dsrc >= sd.sc.dsrc_min && q.dsrc <= sd.sc.dsrc_max; }
+    prop[c] = q;
+    flags[c * 4 + 0] = inb;
+    logu[c] = log(u01(r.z));
+}
+__global__ void k_decide_var(SamplerDev sd, uint32_t sweep, int which, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
+                             double *__restrict__ lsig, const int *__restrict__ flags, const double *__restrict__ logu,
+                             const double *__restrict__ part_prop, int nblk, double *__restrict__ llc,
+                             const unsigned long long *__restrict__ counts)
+{
+    const int c = blockIdx.x;
+    const double pr = reduce_partials(part_prop + (size_t)c * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    const unsigned long long *cn = counts + (size_t)c * NCOUNT;
+    const double d = (pr - llc[c]) + (ll_ext_counts(prop[c], cn) - ll_ext_counts(par[c], cn));
+    int acc = 0;
+    if (flags[c * 4 + 0] && !isnan(d) && logu[c] < d) { acc = 1; par[c] = prop[c]; llc[c] = pr; }
+    if (sweep < (uint32_t)sd.sc.n_adapt) lsig[c * MP_NLSIG + 5 + which] += adapt_gain(sweep) * (acc - 0.44);
+}
 // e and p from the sufficient counts: random-walk MH sub-steps, one thread per chain
 __global__ void k_update_ep(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, double *__restrict__ lsig,
                             const unsigned long long *__restrict__ counts, int nchains)
@@ -414,7 +447,7 @@ __global__ void k_record(SamplerDev sd, const mp_params *__restrict__ par, const
     if (draw) {
         double *d = draw + (size_t)c * MP_NDRAW;
         d[0] = p.e; d[1] = p.c; d[2] = p.alpha; d[3] = p.b; d[4] = p.p; d[5] = le + lc + lp + ld;
-        d[6] = (double)cn[CNT_SY]; d[7] = (double)cn[CNT_SZ];
+        d[6] = (double)cn[CNT_SY]; d[7] = (double)cn[CNT_SZ]; d[8] = p.K; d[9] = p.Ksrc; d[10] = p.dsrc;
     }
     if (parts) { double *q = parts + (size_t)c * MP_NPART; q[0] = le; q[1] = lc; q[2] = lp; q[3] = ld; }
 }

@@ -16,9 +16,9 @@ from . import build as _build
 
 FP32, FP64 = 0, 1
 GEOM_LINEAR, GEOM_COORDS, GEOM_DENSE = 0, 1, 2
-NDRAW, NLSIG, NPART = 8, 5, 4
+NDRAW, NLSIG, NPART = 11, 8, 4
 KERNEL_CATEGORIES = ("conn", "col", "sweep_y", "sweep_z", "small", "sim")
-DRAW_FIELDS = ("e", "c", "alpha", "b", "p", "loglik", "n_y1", "n_z1")
+DRAW_FIELDS = ("e", "c", "alpha", "b", "p", "loglik", "n_y1", "n_z1", "K", "Ksrc", "dsrc")
 
 # every symbol include/libmidaspom_cuda.h declares
 ABI_SYMBOLS = (
@@ -48,9 +48,11 @@ class MpParams(C.Structure):
 
 class MpSamplerConfig(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("e_min", "e_max", "c_min", "c_max", "alpha_min", "alpha_max",
-                                          "b_min", "b_max", "p_min", "p_max")] + \
+                                          "b_min", "b_max", "p_min", "p_max", "K_min", "K_max", "Ksrc_min", "Ksrc_max",
+                                          "dsrc_min", "dsrc_max")] + \
                [(k, C.c_int32) for k in ("sample_e", "sample_c", "sample_alpha", "sample_b", "sample_p",
-                                         "n_e_steps", "n_c_steps", "n_adapt", "update_z", "update_y")]
+                                         "n_e_steps", "n_c_steps", "n_adapt", "update_z", "update_y",
+                                         "sample_K", "sample_Ksrc", "sample_dsrc", "n_v_steps")]
 
 
 PARAM_FIELDS = ("e", "c", "alpha", "b", "p", "K", "Ksrc", "dsrc")
@@ -59,8 +61,9 @@ PARAM_DEFAULTS = dict(e=0.5, c=0.5, alpha=1.0 / 400.0, b=0.0, p=1.0, K=1.0, Ksrc
 
 def sampler_config(**kw) -> MpSamplerConfig:
     d = dict(e_min=0.0, e_max=1.0, c_min=0.0, c_max=1.0, alpha_min=1e-4, alpha_max=1e-1, b_min=0.0, b_max=2.0,
-             p_min=0.0, p_max=1.0, sample_e=1, sample_c=1, sample_alpha=0, sample_b=0, sample_p=0,
-             n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1)
+             p_min=0.0, p_max=1.0, K_min=0.1, K_max=100.0, Ksrc_min=0.1, Ksrc_max=100.0, dsrc_min=200.0, dsrc_max=4000.0,
+             sample_e=1, sample_c=1, sample_alpha=0, sample_b=0, sample_p=0,
+             n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1, sample_K=0, sample_Ksrc=0, sample_dsrc=0, n_v_steps=2)
     d.update(kw)
     return MpSamplerConfig(**d)
 

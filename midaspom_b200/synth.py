@@ -15,6 +15,8 @@ WORKLOADS = {
     # name: (N patches, T years, chains per GPU, imperfect detection)
     "cfg2": dict(n=1000, T=10, chains_per_gpu=8, detect=1, desc="synthetic N=1,000 x T=10, 8 chains, imperfect detection"),
     "cfg3": dict(n=10000, T=20, chains_per_gpu=8, detect=0, desc="synthetic N=10,000 x T=20, 64 chains over 8 GPUs (8 per GPU)"),
+    "cfg4": dict(n=10000, T=20, chains_per_gpu=8, detect=0, era_pre=10, K=3.0,
+                 desc="synthetic N=10,000 x T=20, 8 chains per GPU, die-off variant: first 10 transitions pre-event with K_D=3 (E=e/K, C=c K S), K sampled"),
     "tiny": dict(n=256, T=6, chains_per_gpu=4, detect=0, desc="smoke-test size"),
     "cfg5": dict(n=100000, T=30, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=30, one chain"),
     "cfg5t": dict(n=100000, T=5, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=5, one chain (4 year tasks: what one of 8 GPUs scans in cfg5)"),
@@ -92,11 +94,13 @@ def make_workload(name: str, seed: int = 12345):
     S0 = y0.astype(np.float32) @ W
     c = float(TRUTH["target_mean_C"] / max(S0.mean(), 1e-30))
     y = y0
+    era_pre, Kv = int(w.get("era_pre", 0)), float(w.get("K", 1.0))
     for t in range(T - 1):
-        if t > 0:
-            y = z[t] & (rng.random(n) > e)
+        Kt = Kv if t < era_pre else 1.0                      # die-off variant: E = e/K, C = c K S before the event (dieoff.c:56-57,78)
+        if t > 0 or Kt != 1.0:
+            y = z[t] & (rng.random(n) > min(1.0, e / Kt))
         S = y.astype(np.float32) @ W
-        C = np.minimum(1.0, c * S)
+        C = np.minimum(1.0, c * Kt * S)
         z[t + 1] = np.where(y == 1, 1, rng.random(n) < C)
     obs = z.astype(np.int8)
     if w["detect"]:
@@ -106,5 +110,9 @@ def make_workload(name: str, seed: int = 12345):
     hide[0] = False
     obs[hide] = -1
     truth = dict(e=e, c=c, alpha=alpha, b=b, p=TRUTH["p_detect"] if w["detect"] else 1.0)
-    return dict(name=name, n=n, T=T, px=px, py=py, area=area, obs=obs, z_true=z, truth=truth, detect=w["detect"],
-                chains_per_gpu=w["chains_per_gpu"], desc=w["desc"])
+    out = dict(name=name, n=n, T=T, px=px, py=py, area=area, obs=obs, z_true=z, truth=truth, detect=w["detect"],
+               chains_per_gpu=w["chains_per_gpu"], desc=w["desc"])
+    if era_pre:
+        out["era"] = (np.arange(T - 1) < era_pre).astype(np.uint8)
+        truth["K"] = Kv
+    return out

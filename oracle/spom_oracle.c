@@ -37,7 +37,7 @@ void spom_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[
     memcpy(out, c, sizeof c);
 }
 enum { RK_INIT_PARAM = 1, RK_INIT_Z = 2, RK_SIM_EXT = 3, RK_SIM_COL = 4, RK_Z = 5, RK_Y = 6,
-       RK_AB = 7, RK_C = 8, RK_E = 9, RK_P = 10 };
+       RK_AB = 7, RK_C = 8, RK_E = 9, RK_P = 10, RK_K = 11, RK_KSRC = 12, RK_DSRC = 13 };
 void spom_rng(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t kind, uint32_t a, uint32_t b,
               uint32_t out[4])
 {
@@ -423,6 +423,9 @@ void spom_init_chain(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t 
         if (cfg->sample_b) par->b = cfg->b_min + spom_u01(r[3]) * (cfg->b_max - cfg->b_min);
         spom_rng(seed, chain, 0, RK_INIT_PARAM, 1, 0, r);
         if (cfg->sample_p) par->p = cfg->p_min + spom_u01(r[0]) * (cfg->p_max - cfg->p_min);
+        if (cfg->sample_K) par->K = cfg->K_min * pow(cfg->K_max / cfg->K_min, spom_u01(r[1]));
+        if (cfg->sample_Ksrc) par->Ksrc = cfg->Ksrc_min * pow(cfg->Ksrc_max / cfg->Ksrc_min, spom_u01(r[2]));
+        if (cfg->sample_dsrc) par->dsrc = cfg->dsrc_min + spom_u01(r[3]) * (cfg->dsrc_max - cfg->dsrc_min);
     }
     for (int t = 0; t < T; t++)
         for (int k = 0; k < n; k++) {
@@ -455,6 +458,7 @@ void spom_init_chain(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t 
         if (smax > 0.0 && par->c * smax >= 1.0) { par->c = 0.5 / smax; if (par->c < cfg->c_min) par->c = cfg->c_min; }
     }
     lsig[0] = log(0.05); lsig[1] = log(0.1 * par->c); lsig[2] = log(0.05); lsig[3] = log(0.05); lsig[4] = log(0.05);
+    lsig[5] = log(0.1); lsig[6] = log(0.1); lsig[7] = log(0.1 * (cfg->dsrc_max > cfg->dsrc_min ? cfg->dsrc_max - cfg->dsrc_min : 1.0));
 }
 
 /* Gibbs draws compare logit(u) with the log-odds: u < 1/(1+exp(-d))  <=>  log(u/(1-u)) < d */
@@ -527,6 +531,34 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
             }
             if (adapting) lsig[1] += gain * (acc - 0.44);
         }
+    /* V: variant parameters -- K (pre-event scaling, log-uniform), Ksrc (source size, log-uniform), dsrc (source
+     * distance unit, uniform): random-walk MH, extinction part from the counts, colonisation part over the cells */
+    if (cfg->sample_K || cfg->sample_Ksrc || cfg->sample_dsrc) {
+        int64_t vn10[2], vn11[2], vbad;
+        ext_counts(m, z, y, vn10, vn11, &vbad);
+        for (int which = 0; which < 3; which++) {
+            const int on = which == 0 ? cfg->sample_K : which == 1 ? cfg->sample_Ksrc : cfg->sample_dsrc;
+            if (!on) continue;
+            for (int s = 0; s < cfg->n_v_steps; s++) {
+                double n1, n2;
+                spom_rng(seed, chain, sweep, RK_K + (uint32_t)which, (uint32_t)s, 0, r);
+                box_muller(r[0], r[1], &n1, &n2);
+                const double logu = log(spom_u01(r[2]));
+                spom_params prop = *par;
+                int inb;
+                if (which == 0) { prop.K = par->K * exp(exp(lsig[5]) * n1); inb = prop.K >= cfg->K_min && prop.K <= cfg->K_max; }
+                else if (which == 1) { prop.Ksrc = par->Ksrc * exp(exp(lsig[6]) * n1); inb = prop.Ksrc >= cfg->Ksrc_min && prop.Ksrc <= cfg->Ksrc_max; }
+                else { prop.dsrc = par->dsrc + exp(lsig[7]) * n1; inb = prop.dsrc >= cfg->dsrc_min && prop.dsrc <= cfg->dsrc_max; }
+                int acc = 0;
+                if (inb) {
+                    const double llc2 = ll_col_all(m, &prop, z, y, S);
+                    const double d = (llc2 - llc) + (ll_ext_counts(&prop, vn10, vn11, vbad) - ll_ext_counts(par, vn10, vn11, vbad));
+                    if (mh_accept(logu, d)) { acc = 1; *par = prop; llc = llc2; }
+                }
+                if (adapting) lsig[5 + which] += gain * (acc - 0.44);
+            }
+        }
+    }
     /* D: latent z cells -- conditionally independent given y (S depends on y only) */
     if (cfg->update_z) {
         const double p0 = prior_p0(m);
@@ -637,7 +669,7 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
         draw[0] = par->e; draw[1] = par->c; draw[2] = par->alpha; draw[3] = par->b; draw[4] = par->p;
         draw[5] = ll_ext_counts(par, n10, n11, bad) + ll_col_all(m, par, z, y, S) + ll_prior(m, z)
                 + ll_det_counts(m, par, nd, nm, bad2);
-        draw[6] = (double)sy; draw[7] = (double)sz;
+        draw[6] = (double)sy; draw[7] = (double)sz; draw[8] = par->K; draw[9] = par->Ksrc; draw[10] = par->dsrc;
     }
     if (phase_s) { phase_s[0] = now_s() - t_begin - t_yscan; phase_s[1] = t_yscan; }
     return visited;

@@ -57,14 +57,16 @@ typedef struct { double e, c, alpha, b, p, K, Ksrc, dsrc; } spom_params;
 
 typedef struct {
     double e_min, e_max, c_min, c_max, alpha_min, alpha_max, b_min, b_max, p_min, p_max;
+    double K_min, K_max, Ksrc_min, Ksrc_max, dsrc_min, dsrc_max;
     int32_t sample_e, sample_c, sample_alpha, sample_b, sample_p;
     int32_t n_e_steps, n_c_steps;
     int32_t n_adapt;            /* sweeps during which proposal scales adapt */
     int32_t update_z, update_y;
+    int32_t sample_K, sample_Ksrc, sample_dsrc, n_v_steps;
 } spom_sampler_cfg;
 
-#define SPOM_NDRAW 8   /* e, c, alpha, b, p, loglik, #y=1, #z=1 */
-#define SPOM_NLSIG 5   /* log proposal scales: e, c, alpha, b, p */
+#define SPOM_NDRAW 11  /* e, c, alpha, b, p, loglik, #y=1, #z=1, K, Ksrc, dsrc */
+#define SPOM_NLSIG 8   /* log proposal scales: e, c, alpha, b, p, K, Ksrc, dsrc */
 
 /* ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG shared with the CUDA engine ---- */
 void   spom_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -19,8 +19,8 @@ ORACLE_SO = ORACLE_DIR / "libspom_oracle.so"
 REF_SO = ORACLE_DIR / "_ref" / "libmidaspom_ref.so"
 REF_BIN = ORACLE_DIR / "_ref"
 
-NDRAW = 8
-NLSIG = 5
+NDRAW = 11
+NLSIG = 8
 GEOM_LINEAR, GEOM_COORDS, GEOM_DENSE = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -41,9 +41,11 @@ class SpomParams(C.Structure):
 
 class SpomSamplerCfg(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("e_min", "e_max", "c_min", "c_max", "alpha_min", "alpha_max",
-                                          "b_min", "b_max", "p_min", "p_max")] + \
+                                          "b_min", "b_max", "p_min", "p_max", "K_min", "K_max", "Ksrc_min", "Ksrc_max",
+                                          "dsrc_min", "dsrc_max")] + \
                [(k, C.c_int32) for k in ("sample_e", "sample_c", "sample_alpha", "sample_b", "sample_p",
-                                         "n_e_steps", "n_c_steps", "n_adapt", "update_z", "update_y")]
+                                         "n_e_steps", "n_c_steps", "n_adapt", "update_z", "update_y",
+                                         "sample_K", "sample_Ksrc", "sample_dsrc", "n_v_steps")]
 
 
 def build_oracle(force: bool = False) -> None:
@@ -120,8 +122,9 @@ def params(e=0.5, c=0.5, alpha=1.0 / 400, b=0.0, p=1.0, K=1.0, Ksrc=0.0, dsrc=0.
 
 def sampler_cfg(**kw) -> SpomSamplerCfg:
     d = dict(e_min=0.0, e_max=1.0, c_min=0.0, c_max=1.0, alpha_min=1e-4, alpha_max=1e-1, b_min=0.0, b_max=2.0,
-             p_min=0.0, p_max=1.0, sample_e=1, sample_c=1, sample_alpha=0, sample_b=0, sample_p=0,
-             n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1)
+             p_min=0.0, p_max=1.0, K_min=0.1, K_max=100.0, Ksrc_min=0.1, Ksrc_max=100.0, dsrc_min=200.0, dsrc_max=4000.0,
+             sample_e=1, sample_c=1, sample_alpha=0, sample_b=0, sample_p=0,
+             n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1, sample_K=0, sample_Ksrc=0, sample_dsrc=0, n_v_steps=2)
     d.update(kw)
     return SpomSamplerCfg(**d)
 

@@ -374,6 +374,38 @@ def test_sharded_chain_equals_single_engine():
         e.close()
 
 
+@pytest.mark.parametrize("variant", ["dieoff", "loss"])
+def test_fp64_variant_sampling_follows_the_cpu_twin(variant):
+    """Pre-event years with the die-off scaling K (dieoff.c:56-57,78) or the external source K_L, d_L
+    (loss.c:93-101,365), the variant parameters SAMPLED: FP64 engine == CPU twin, draw by draw."""
+    rng = np.random.default_rng(123)
+    n, T, C = 80, 8, 3
+    spec, z, _ = random_landscape(rng, n, T, O.GEOM_LINEAR, occ=0.5, miss=0.06, areas=False)
+    spec["era"] = (np.arange(T - 1) < 4).astype(np.uint8)
+    m = make_model(spec)
+    if variant == "dieoff":
+        kw = dict(sample_K=1, K_min=0.1, K_max=100.0)
+        par0 = pdict(e=0.4, c=0.2, alpha=1 / 400, K=2.0)
+    else:
+        kw = dict(sample_Ksrc=1, sample_dsrc=1, Ksrc_min=0.1, Ksrc_max=100.0, dsrc_min=5.0, dsrc_max=400.0)
+        par0 = pdict(e=0.4, c=0.2, alpha=1 / 400, K=1.0, Ksrc=2.0, dsrc=60.0)
+    kw.update(c_max=2.0, n_adapt=6, n_v_steps=2)
+    nsw, seed = 10, 77
+    ch = O.Chains(m, O.sampler_cfg(**kw), C, seed=seed, par0=oparams(par0), disperse=False)
+    want = ch.run(nsw)
+    with make_engine(spec, n_chains=C, seed=seed, max_draws=nsw) as eng:
+        eng.set_params([par0] * C)
+        eng.init_chains(mb.engine.sampler_config(**kw), disperse=False)
+        eng.sweep(nsw)
+        got = eng.get_draws()
+        zg, yg = eng.get_state()
+    assert (zg == ch.z).all() and (yg == ch.y).all()
+    rel_close(got[:, :, [0, 1, 8, 9, 10]], want[:, :, [0, 1, 8, 9, 10]], 1e-9)
+    rel_close(got[:, :, 5], want[:, :, 5], 1e-9, floor=1.0)
+    moved = 8 if variant == "dieoff" else 9
+    assert np.unique(got[:, :, moved]).size > 3                     # the variant parameter actually moves
+
+
 def test_chain_offset_selects_the_stream():
     """A chain's random stream depends on its GLOBAL id only: chains [2,3] run alone reproduce
     chains 2,3 of a 4-chain engine (the property MIDASPOM_MPI's row split relies on, :361-372)."""
