@@ -49,11 +49,11 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     a.k_lo = h->conn_lo; a.k_hi = h->conn_hi < 0 ? h->cfg.n_patches : h->conn_hi;
     if (a.k_hi <= a.k_lo) return MP_OK;
     dim3 grid((a.k_hi - a.k_lo + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
-    const int ny = a.ntrans;
-    if (ny <= 8) k_conn<R, GEOM, 8><<<grid, CONN_TILE, 0, h->stream>>>(a);
-    else if (ny <= 16) k_conn<R, GEOM, 16><<<grid, CONN_TILE, 0, h->stream>>>(a);
-    else if (ny <= 24) k_conn<R, GEOM, 24><<<grid, CONN_TILE, 0, h->stream>>>(a);
-    else k_conn<R, GEOM, 32><<<grid, CONN_TILE, 0, h->stream>>>(a);
+    const int ny = a.ntrans;                          // year accumulators per target: next multiple of 4 (<= 32 per pass)
+#define MP_CONN(NYB) k_conn<R, GEOM, NYB><<<grid, CONN_TILE, 0, h->stream>>>(a)
+    if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
+    else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);
+#undef MP_CONN
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -241,7 +241,9 @@ template <typename R> static int phase_decide_z(mp_engine *h)
     const long long cells = (long long)ycells(h);
     if (do_ab) {
         Timed tm(h, MP_K_SMALL);
-        k_ridge_c<<<C, 256, 0, h->stream>>>(sd, h->d_par, h->d_prop, h->d_S[0], h->d_S[1], cells, h->d_flags, h->d_ljac);
+        k_sum_S<<<dim3(h->nblk_col, C, 2), COL_THREADS, 0, h->stream>>>(h->d_S[0], h->d_S[1], cells, h->d_partial[0], h->d_partial[1]);
+        CK(cudaGetLastError());
+        k_ridge_c<<<C, 32, 0, h->stream>>>(sd, h->d_par, h->d_prop, h->d_partial[0], h->d_partial[1], h->nblk_col, h->d_flags, h->d_ljac);
         CK(cudaGetLastError());
     }
     if ((rc = launch_col<R>(h, do_ab ? 2 : 1, h->d_par, h->d_S[0], h->d_prop, h->d_S[1])) != MP_OK) return rc;

@@ -270,17 +270,24 @@ __global__ void k_propose_ab(SamplerDev sd, uint32_t sweep, const mp_params *__r
 // c' = c mean(S)/mean(S') -- a deterministic, reversible shift of log c (mean S depends on (alpha, b, y)
 // only) -- and the Hastings ratio gains the Jacobian c'/c of the uniform-in-c prior seen in log c.
 // One CTA per chain; fixed-order sums.  ljac[c] = log(c'/c); flags[c*4+0] &= c' within bounds.
-__global__ void __launch_bounds__(256)
-k_ridge_c(SamplerDev sd, const mp_params *__restrict__ par, mp_params *__restrict__ prop, const double *__restrict__ S,
-          const double *__restrict__ S2, long long cells, int *__restrict__ flags, double *__restrict__ ljac)
-{
+__global__ void __launch_bounds__(COL_THREADS)
+k_sum_S(const double *__restrict__ S, const double *__restrict__ S2, long long cells, double *__restrict__ part0,
+        double *__restrict__ part1)
+{   // grid (nblk, chains, 2): partial sums of S (set 0) and S' (set 1), same block->cell map as k_col_ll
     __shared__ double scratch[32];
+    const int c = blockIdx.y;
+    const double *src = (blockIdx.z ? S2 : S) + (size_t)c * cells;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * COL_THREADS + threadIdx.x; i < cells; i += (long long)gridDim.x * COL_THREADS) acc += src[i];
+    const double tot = block_sum(acc, scratch);
+    if (threadIdx.x == 0) (blockIdx.z ? part1 : part0)[(size_t)c * gridDim.x + blockIdx.x] = tot;
+}
+__global__ void k_ridge_c(SamplerDev sd, const mp_params *__restrict__ par, mp_params *__restrict__ prop,
+                          const double *__restrict__ part0, const double *__restrict__ part1, int nblk,
+                          int *__restrict__ flags, double *__restrict__ ljac)
+{   // one warp per chain
     const int c = blockIdx.x;
-    double m1 = 0.0, m2 = 0.0;
-    for (long long i = threadIdx.x; i < cells; i += blockDim.x) { m1 += S[(size_t)c * cells + i]; m2 += S2[(size_t)c * cells + i]; }
-    m1 = block_sum(m1, scratch);
-    __syncthreads();
-    m2 = block_sum(m2, scratch);
+    const double m1 = reduce_partials(part0 + (size_t)c * nblk, nblk), m2 = reduce_partials(part1 + (size_t)c * nblk, nblk);
     if (threadIdx.x != 0) return;
     double lj = 0.0;
     if (sd.sc.sample_c && m1 > 0.0 && m2 > 0.0) {
