@@ -259,7 +259,7 @@ def run_ours(args, rank, local_rank, world):
         mufu_per_pair = 2.2                                                   # MUFU.SQRT + MUFU.EX2 + MUFU.LG2 / 5 (planar geometry)
         alg_bytes = cpg * (T - 1) * n * (8 + 1 + 1 + 1 + 8 + 1) + cpg * ncand * 32   # S,y,z_t,z_t+1 in; S,y out; candidate records
         t_conn = kms["conn"] / max(1, klaunch["conn"]) * 1e-3
-        conn_pairs = cpg * 2 * float(n) * n                                   # current + proposal parameter sets
+        conn_pairs = cpg * float(n) * n * (klaunch['conn'] and (1.0 + 1.0 / 16.0))   # proposal every sweep + resident S every 16th
         traffic = None                                                        # dram read+write per launch, from the tracked ncu summary
         for f in sorted((ROOT / "profiles").glob("*_ncu_full.json"), reverse=True):
             for kd in json.loads(f.read_text()):

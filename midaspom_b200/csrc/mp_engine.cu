@@ -136,14 +136,16 @@ static int launch_sweep_y_fast(mp_engine *h)
         CK(cudaGetLastError());
     }
     Timed tm(h, MP_K_SWEEP_Y);
-    int tpt = h->fast_tpt ? h->fast_tpt : (n > 6144 ? 512 : 1024);   // threads per task
+    // threads per task, from measurements: 256 (one CTA, no DSMEM) up to 3,000 patches (cfg2: 0.27 vs 0.35 ms),
+    // 512 up to 15,872 (cfg3: 15.5 vs 18.7 ms for 1024)
+    int tpt = h->fast_tpt ? h->fast_tpt : (n <= 3000 ? 256 : 512);
     if ((n + tpt - 1) / tpt > 31) tpt = 1024;
     for (int big = 2048; (n + tpt - 1) / tpt > 31 && big <= 8192; big *= 2) tpt = big;   // N > 31k: 2048..8192 threads, cluster of 8
     // large landscapes: a cluster of 8 holds the task's state; with few tasks per GPU (year sharding) spread each
     // task over 16 SMs instead -- the scan is latency-bound per flip
     const int ntask_own = (C * ntrans - h->task_first + h->task_stride - 1) / h->task_stride;
     const int cs = tpt > 1024 ? (h->fast_cs == 16 || (h->fast_cs == 0 && tpt >= 4096 && ntask_own * 16 <= h->sm_count) ? 16 : 8)
-                              : (h->fast_cs ? h->fast_cs : pick_cluster(C * ntrans, h->sm_count, 8));
+                              : (h->fast_cs ? h->fast_cs : (tpt == 256 ? 1 : pick_cluster(C * ntrans, h->sm_count, 8)));
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
     case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);
@@ -383,7 +385,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     h->cfg = *cfg;
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
-    if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
+    if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
     h->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char *what, cudaError_t ce) {
         g_create_error = std::string("mp_create: ") + what + ": " + cudaGetErrorString(ce);

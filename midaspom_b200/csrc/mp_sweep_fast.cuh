@@ -405,6 +405,8 @@ static int launch_fast_any(mp_engine *h, int cs, int tpt)
         if (tpt == 4096) return cs == 16 ? launch_fast_u<16, 4096>(h, ept) : launch_fast_u<8, 4096>(h, ept);
         return cs == 16 ? launch_fast_u<16, 8192>(h, ept) : launch_fast_u<8, 8192>(h, ept);
     }
+    if (tpt == 256) return cs >= 2 ? launch_fast_u<2, 256>(h, ept) : launch_fast_u<1, 256>(h, ept);   // small landscapes
+    if (tpt == 128) return launch_fast_u<1, 128>(h, ept);
     if (tpt == 512) switch (cs) {
         case 1: return launch_fast_u<1, 512>(h, ept);
         case 2: return launch_fast_u<2, 512>(h, ept);
