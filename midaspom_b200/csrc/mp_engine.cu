@@ -132,7 +132,7 @@ static int launch_sweep_y_fast(mp_engine *h)
         k_build_candidates<<<ntask, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
                                                            (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
                                                            h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS,
-                                                           h->task_first, h->task_stride);
+                                                           h->task_first, h->task_stride, h->d_inv);
         CK(cudaGetLastError());
     }
     Timed tm(h, MP_K_SWEEP_Y);
@@ -146,6 +146,9 @@ static int launch_sweep_y_fast(mp_engine *h)
     const int ntask_own = (C * ntrans - h->task_first + h->task_stride - 1) / h->task_stride;
     const int cs = tpt > 1024 ? (h->fast_cs == 16 || (h->fast_cs == 0 && tpt >= 4096 && ntask_own * 16 <= h->sm_count) ? 16 : 8)
                               : (h->fast_cs ? h->fast_cs : (tpt == 256 ? 1 : pick_cluster(C * ntrans, h->sm_count, 8)));
+    // exact spatial culling of the evaluation (mp_sweep_cull.cuh) where positions exist and the landscape is large
+    if (h->fast_cull && h->geom != MP_GEOM_DENSE && (tpt == 512 || tpt >= 2048))
+        return h->geom == MP_GEOM_LINEAR ? mp_launch_sweep_cull_linear(h, cs, tpt) : mp_launch_sweep_cull_coords(h, cs, tpt);
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
     case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);
@@ -352,7 +355,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_ljac };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_ljac, h->d_perm, h->d_inv };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -383,6 +386,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     }
     mp_engine *h = new mp_engine();
     h->cfg = *cfg;
+    if (const char *env = getenv("MP_FAST_CULL")) h->fast_cull = atoi(env) != 0;
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
@@ -413,6 +417,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) },
+        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_inv, N * sizeof(int) },
     };
     for (auto &r : reqs) {
         if ((e = cudaMalloc(r.p, r.bytes)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -447,6 +452,31 @@ static int set_area(mp_engine *h, const double *area)
     }
     return MP_OK;
 }
+// Morton (Z-order) permutation of the patches: perm[slot] = patch, inv[patch] = slot.  Spatially adjacent
+// patches get adjacent slots, which is what makes the warp-level culling of k_sweep_y_cull effective.
+static int set_patch_order(mp_engine *h, const double *x, const double *y)
+{
+    const size_t N = nN(h);
+    std::vector<int> perm(N), inv(N);
+    for (size_t i = 0; i < N; i++) perm[i] = (int)i;
+    if (x && y) {
+        double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
+        for (size_t i = 1; i < N; i++) { x0 = std::min(x0, x[i]); x1 = std::max(x1, x[i]); y0 = std::min(y0, y[i]); y1 = std::max(y1, y[i]); }
+        const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
+        auto spread = [](uint32_t v) { v &= 0xffffu; v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu;
+                                       v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u; return v; };
+        std::vector<uint32_t> code(N);
+        for (size_t i = 0; i < N; i++) {
+            const uint32_t xi = (uint32_t)std::min(65535.0, (x[i] - x0) / span * 65535.0), yi = (uint32_t)std::min(65535.0, (y[i] - y0) / span * 65535.0);
+            code[i] = spread(xi) | (spread(yi) << 1);
+        }
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return code[a] < code[b]; });
+    }
+    for (size_t s = 0; s < N; s++) inv[perm[s]] = (int)s;
+    CK(cudaMemcpy(h->d_perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_inv, inv.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    return MP_OK;
+}
 int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
 {
     if (!h) return MP_ERR_ARG;
@@ -454,7 +484,9 @@ int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
     if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(spacing > 0.0, MP_ERR_ARG, "spacing must be positive");
     h->geom = MP_GEOM_LINEAR; h->spacing = spacing;
-    int rc = set_area(h, area);
+    int rc = set_patch_order(h, nullptr, nullptr);      // a line is already in spatial order
+    if (rc != MP_OK) return rc;
+    rc = set_area(h, area);
     if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;
 }
@@ -468,6 +500,7 @@ int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, cons
     int rc;
     if ((rc = upload_real(h, h->d_px, x, nN(h))) != MP_OK) return rc;
     if ((rc = upload_real(h, h->d_py, y, nN(h))) != MP_OK) return rc;
+    if ((rc = set_patch_order(h, x, y)) != MP_OK) return rc;
     rc = set_area(h, area);
     if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;
@@ -483,6 +516,7 @@ int mp_set_landscape_dense(mp_engine *h, const double *dist, const double *area)
     h->geom = MP_GEOM_DENSE;
     int rc;
     if ((rc = upload_real(h, h->d_dist, dist, nn)) != MP_OK) return rc;
+    if ((rc = set_patch_order(h, nullptr, nullptr)) != MP_OK) return rc;
     rc = set_area(h, area);
     if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;

@@ -54,6 +54,8 @@ struct mp_engine {
     bool S_valid = false;            // resident S corresponds to the resident (y, alpha, b)
     int task_first = 0, task_stride = 1;   // (chain, year) tasks of the y sweep run by this engine (year sharding)
     int conn_lo = 0, conn_hi = -1;        // target patches of k_conn run by this engine (patch sharding); hi < 0 = all
+    int *d_perm = nullptr, *d_inv = nullptr;   // Morton order of the patches: perm[slot] = patch, inv[patch] = slot
+    int fast_cull = 1;               // exact spatial culling in the fast sweep (MP_FAST_CULL=0 disables)
     int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides
     int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
     // timing
@@ -130,3 +132,5 @@ template <typename R> inline mp::Landscape<R> view(const mp_engine *h)
 int mp_launch_sweep_fast_linear(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_fast_coords(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_fast_dense(mp_engine *h, int cs, int tpt);
+int mp_launch_sweep_cull_linear(mp_engine *h, int cs, int tpt);
+int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt);

@@ -1,0 +1,389 @@
+// mp_sweep_cull.cuh -- the FP32 fast y scan (mp_sweep_fast.cuh) with EXACT spatial culling of the evaluation.
+//
+// Targets are laid out in Morton order (perm[slot] = patch): thread g owns slots g, g+TPT, ..., so the 32
+// lanes of a warp hold, for every j, 32 spatially adjacent patches -- a "group" with a bounding circle
+// (centre, radius) and a lower bound mlow on its S values.  For a candidate k the dispersal weight of every
+// target of a group is at most wub = A_k^b exp(-alpha max(0, |centre - k| - radius)).  If wub < 2^-26 mlow then
+// fl(S_hi +- w) = S_hi for every target of the group: the factor ratio is exactly 1 and the group's lg2
+// contribution exactly 0 -- the whole slot is skipped for the warp, with no approximation (a chain's path
+// is that of the unculled kernel up to FP32 ties).  With landscapes much wider than the dispersal range
+// (cfg3: 25 km vs 1/alpha = 0.4 km) most groups are skipped.  The commit skips a group when wub < 2^-36 mlow:
+// the skipped mass, summed over all commits between two refreshes of S (every 16 sweeps), stays orders of
+// magnitude below the FP32 resolution of S (measured drift of S against k_conn: tests/test_gpu_parity.py).
+//
+// Differences from k_sweep_y_fast:
+//  * candidate records carry the candidate's Morton slot and are staged through a two-chunk ring in shared memory;
+//  * the denominator product is formed on the fly over the evaluated slots (no cached D);
+//  * lane j of every warp keeps the bounds of the warp's group j in registers; a removal recomputes the exact
+//    min S of every group it commits to with one REDUX (S_hi >= 0, so the IEEE bit pattern orders like the value);
+//  * the evaluated slots are taken from the ballot mask in batches of up to 4 independent dependency chains;
+//  * every trip evaluates two candidates (i and, speculatively, i+1) and reduces both sums in ONE exchange:
+//    a rejected flip (2 of 3) costs no reduction latency of its own.  The decisions are exactly those of the
+//    one-at-a-time scan: B's sum is used only if A left the state unchanged.
+#pragma once
+#include "mp_sweep_fast.cuh"
+
+namespace mp {
+
+#ifdef MP_DEBUG_CULL
+__device__ unsigned long long g_cull_dbg[4];   // [0] warp-flips, [1] evaluated slots, [2] total slots, [3] committed slots
+#endif
+
+template <int GEOM, int CS, int TPT>
+__global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
+k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_params *__restrict__ par,
+               const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, int task_first, int task_stride)
+{
+    static_assert(GEOM != MP_GEOM_DENSE, "culling needs positions");
+    constexpr int NT = TPT / CS, NW = NT / 32;
+    constexpr bool HIER = TPT / 32 > 32;
+    constexpr int NSLOT = HIER ? CS : TPT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) float2 red[2][2][32];
+    __shared__ __align__(8) float2 wred[HIER ? 2 : 1][2][32];
+    __shared__ __align__(8) unsigned long long mbar[2][2];
+    const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
+    const int task = task_first + (blockIdx.x / CS) * task_stride;
+    const int c = task / ntrans, t = task - c * ntrans;
+    float4 *sT = reinterpret_cast<float4 *>(smem_raw);               // {S_hi, S_lo, x, y} (COORDS) or {S_hi, S_lo, patch, -} (LINEAR)
+    float4 *ring = sT + ept * NT;                                    // 2 chunks of RC candidate records (two float4 each)
+
+    const Trans<float> tr = make_trans<float>(par[c], era ? era[t] : 0);
+    const float cK = tr.c * tr.Kt;
+    const float nal2e = alpha_pre<float>(par[c].alpha);
+    const double src_scale = tr.src ? (double)tr.Ks / (double)tr.Kt : 0.0;
+    auto src_offset = [&](int q) -> double {
+        if (!tr.src) return 0.0;
+        const double u = ls.src_unit ? ls.src_unit[q] : (double)(q + 1);
+        return src_scale * exp(-(par[c].alpha * u) * par[c].dsrc);
+    };
+    uint8_t *yt = y + ((size_t)c * ntrans + t) * n;
+    const uint8_t *zn = z + ((size_t)c * T + t + 1) * n;
+    double *St = S + ((size_t)c * ntrans + t) * n;
+
+    const int g = (int)rank * NT + tid;
+    uint32_t Amask = 0, Bmask = 0, ybits = 0, valid = 0;
+    // lane j of every warp keeps the bounds of the warp's group j: COORDS {centre x, centre y, radius}, LINEAR {first, last patch}; Gw = min S
+    float Gx = 0.f, Gy = 0.f, Gr = 3.0e38f, Gw = 0.f;
+    for (int j = 0; j < ept; j++) {
+        const int s = g + j * TPT;
+        const int q = s < n ? perm[s] : -1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q >= 0) {
+            if (GEOM == MP_GEOM_COORDS) { v.z = ls.px[q]; v.w = ls.py[q]; }
+            else v.z = __int_as_float(q);
+            const double sv = St[q] + src_offset(q);
+            v.x = (float)sv; v.y = (float)(sv - (double)v.x);
+            const uint32_t yq = yt[q] != 0, zq = zn[q] != 0;
+            ybits |= yq << j; Amask |= ((yq ^ 1u) & zq) << j; Bmask |= ((yq ^ 1u) & (zq ^ 1u)) << j; valid |= 1u << j;
+        }
+        sT[tid + j * NT] = v;
+        const float big = 3.0e38f;
+        float a0, a1, b0, b1, ml = q >= 0 ? v.x : big;
+        if (GEOM == MP_GEOM_COORDS) { a0 = q >= 0 ? v.z : big; a1 = q >= 0 ? v.z : -big; b0 = q >= 0 ? v.w : big; b1 = q >= 0 ? v.w : -big; }
+        else { a0 = q >= 0 ? (float)q : big; a1 = q >= 0 ? (float)q : -big; b0 = 0.f; b1 = 0.f; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 = fminf(a0, __shfl_xor_sync(0xffffffffu, a0, o)); a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+            b0 = fminf(b0, __shfl_xor_sync(0xffffffffu, b0, o)); b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+            ml = fminf(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+        }
+        if (lane == j) {
+            if (a0 > a1) { Gx = 0.f; Gy = 0.f; Gr = 3.0e38f; Gw = 0.f; }     // empty group: every factor is 1 anyway
+            else if (GEOM == MP_GEOM_COORDS) { const float dx = a1 - a0, dy = b1 - b0;
+                                               Gx = 0.5f * (a0 + a1); Gy = 0.5f * (b0 + b1); Gr = 0.5000005f * sqrtf(dx * dx + dy * dy) + 1e-3f; Gw = ml; }
+            else { Gx = a0; Gy = a1; Gr = 0.f; Gw = ml; }
+        }
+    }
+    if (CS > 1) {
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) mbar_init(smem_u32(&mbar[i >> 1][i & 1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        cluster_barrier();
+    } else __syncthreads();
+    const uint32_t red_remote = CS > 1 ? map_to_rank(smem_u32(&red[0][0][0]), (uint32_t)(lane < CS ? lane : 0)) : 0u;
+    const uint32_t bar_remote = CS > 1 ? map_to_rank(smem_u32(&mbar[0][0]), (uint32_t)(lane < CS ? lane : 0)) : 0u;
+    const uint32_t bar_local = smem_u32(&mbar[0][0]);
+    const int ncand = count[2 * task];
+    int nocc = count[2 * task + 1];
+    const CandRec *recs = rec + (size_t)task * n;
+    uint32_t uses[2] = { 0u, 0u };
+
+    // sum of a pair of per-thread values over the task's TPT threads (warp shuffles, then st.async of the warp or
+    // CTA partial to every CTA of the cluster, completion counted on the destination's mbarrier)
+    auto all_reduce = [&](int round, float2 v) -> float2 {
+        const uint32_t u = uses[round]++;
+        const int p = u & 1;
+        v.x = warp_sum_f(v.x); v.y = warp_sum_f(v.y);
+        if (HIER) {
+            if (lane == 0) wred[round][p][wid] = v;
+            __syncthreads();
+            const float2 t = lane < NW ? wred[round][p][lane] : make_float2(0.f, 0.f);
+            v.x = warp_sum_f(t.x); v.y = warp_sum_f(t.y);
+        }
+        if (CS > 1) {
+            const uint32_t boff = (uint32_t)(round * 2 + p) * 8u;
+            const uint32_t slot = HIER ? rank : rank * NW + wid;
+            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)slot) * 8u;
+            if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 8);
+            if (lane < CS && (!HIER || wid == 0)) st_async_f32x2(red_remote + roff, v, bar_remote + boff);
+            mbar_wait(bar_local + boff, (u >> 1) & 1u);
+            const float2 t = lane < NSLOT ? red[round][p][lane] : make_float2(0.f, 0.f);
+            return make_float2(warp_sum_f(t.x), warp_sum_f(t.y));
+        }
+        if (HIER) return v;
+        if (lane == 0) red[round][p][wid] = v;
+        __syncthreads();
+        const float2 t = lane < NSLOT ? red[round][p][lane] : make_float2(0.f, 0.f);
+        return make_float2(warp_sum_f(t.x), warp_sum_f(t.y));
+    };
+    // weight of (candidate k, target in slot data tq)
+    auto weight = [&](const float4 &tq, int k, float kx, float ky, float lawk) -> float {
+        float d;
+        if (GEOM == MP_GEOM_LINEAR) { const int q = __float_as_int(tq.z); d = (float)(q > k ? q - k : k - q) * ls.spacing; }
+        else { const float dx = tq.z - kx, dy = tq.w - ky; d = Num<float>::sqrtv(fmaf(dx, dx, dy * dy)); }
+        return weight_of(nal2e, lawk, d);
+    };
+
+    // upper bound of the weights of candidate (k; kx, ky) on this lane's group (margins cover the rounding of the bound itself)
+    auto group_bound = [&](int k, float kx, float ky, float lawk) -> float {
+        float dlow;
+        if (GEOM == MP_GEOM_COORDS) { const float dx = Gx - kx, dy = Gy - ky; dlow = fmaxf(0.f, Num<float>::sqrtv(fmaf(dx, dx, dy * dy)) - Gr); }
+        else dlow = ls.spacing * fmaxf(0.f, fmaxf(Gx - (float)k, (float)k - Gy));
+        return 1.001f * weight_of(nal2e, lawk, 0.99999f * dlow);     // sqrt.approx, ex2.approx: a few ulp each
+    };
+    auto own_term = [&](int kj, uint32_t cur) -> float {
+        const float4 tq = sT[tid + kj * NT];
+        const float lg2e = 1.4426950408889634f;
+        const float l0 = lg2e * tr.logE + Num<float>::lg2(__saturatef(cK * (tq.x + tq.y)));
+        const float l1 = lg2e * tr.log1mE;
+        return cur ? ldiff<float>(l0, l1) : ldiff<float>(l1, l0);
+    };
+
+    // ---- candidate records travel through a two-chunk ring in shared memory (chunks c and c+1 resident while i is in chunk c)
+    constexpr int RC = 32;
+    const float4 *recs4 = reinterpret_cast<const float4 *>(recs);
+    auto load_chunk = [&](int cidx) -> float4 {
+        const int idx = cidx * RC * 2 + tid;
+        return (tid < 2 * RC && idx < 2 * ncand) ? recs4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 pre;
+    {
+        const float4 c0 = load_chunk(0), c1 = load_chunk(1);
+        pre = load_chunk(2);
+        if (tid < 2 * RC) { ring[tid] = c0; ring[2 * RC + tid] = c1; }
+        __syncthreads();
+    }
+    int chunk = 0;
+    struct Cand { int k; uint32_t cur; float kx, ky, lawk, thr; int kslot; };
+    auto read_cand = [&](int i) -> Cand {
+        const float4 a = ring[(i & (2 * RC - 1)) * 2], b = ring[(i & (2 * RC - 1)) * 2 + 1];
+        Cand cd;
+        cd.k = (int)(__float_as_uint(a.x) & 0x7fffffffu); cd.cur = __float_as_uint(a.x) >> 31;
+        cd.kx = a.y; cd.ky = a.z; cd.lawk = a.w; cd.thr = b.x; cd.kslot = (int)__float_as_uint(b.y);
+        return cd;
+    };
+    auto bound_of = [&](int i) -> float {
+        const float4 a = ring[(i & (2 * RC - 1)) * 2];
+        return group_bound((int)(__float_as_uint(a.x) & 0x7fffffffu), a.y, a.z, a.w);
+    };
+    // lg2 of the likelihood ratio of flipping candidate cd, this thread's share (evaluated groups only)
+    auto evaluate = [&](const Cand &cd, uint32_t active, bool own, int kj, uint32_t Ae, uint32_t Be) -> float {
+        const float sgn = cd.cur ? -1.f : 1.f;
+        float acc2 = 0.f;
+        uint32_t m = active;
+        // B independent (sqrt, ex2, 2 x FFMA.SAT) chains per trip
+        auto batch = [&](auto BB) {
+            constexpr int B = decltype(BB)::value;
+            float pn = 1.f, pd = 1.f;
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int j = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const float4 tq = sT[tid + j * NT];
+                const float w = weight(tq, cd.k, cd.kx, cd.ky, cd.lawk);
+                // class A (z'=1): sat(cK S); class B (z'=0): sat(1 - cK S); neither: 1 -- as one FFMA.SAT with selected constants
+                const bool a = (Ae >> j) & 1u, b = (Be >> j) & 1u;
+                const float mul = a ? cK : (b ? -cK : 0.f), add = a ? 0.f : 1.f;
+                pn *= __saturatef(fmaf(mul, fmaf(sgn, w, tq.x) + tq.y, add));
+                pd *= __saturatef(fmaf(mul, tq.x + tq.y, add));
+            }
+            acc2 += Num<float>::lg2(pn) - Num<float>::lg2(pd);
+        };
+        while (m) {                                       // warp-uniform
+            const int left = __popc(m);
+            if (left >= 4) batch(std::integral_constant<int, 4>());
+            else if (left == 3) batch(std::integral_constant<int, 3>());
+            else if (left == 2) batch(std::integral_constant<int, 2>());
+            else batch(std::integral_constant<int, 1>());
+        }
+        if (own) acc2 += own_term(kj, cd.cur);
+        return acc2;
+    };
+    // cell-by-cell evaluation with the (-inf) - (-inf) := 0 convention (impossible current state, removal of the last occupied patch)
+    auto evaluate_careful = [&](const Cand &cd, bool zero_after, bool own, int kj, uint32_t Ae, uint32_t Be) -> float {
+        const float sgn = cd.cur ? -1.f : 1.f;
+        float acc2 = 0.f;
+        for (int j = 0; j < ept; j++) {
+            const bool a = (Ae >> j) & 1u, b = (Be >> j) & 1u;
+            if (!(a || b)) continue;
+            const float4 tq = sT[tid + j * NT];
+            const int s = g + j * TPT;
+            const float w = weight(tq, cd.k, cd.kx, cd.ky, cd.lawk);
+            const float sa = zero_after ? (float)src_offset(perm[s]) : fmaf(sgn, w, tq.x) + tq.y;
+            acc2 += ldiff<float>(Num<float>::lg2(col_factor(cK, sa, a, b)), Num<float>::lg2(col_factor(cK, tq.x + tq.y, a, b)));
+        }
+        if (own) acc2 += own_term(kj, cd.cur);
+        return acc2;
+    };
+    auto commit = [&](const Cand &cd, float wub, bool zero_after, bool own, int kj, uint32_t ownbit) {
+        if (own) { ybits ^= ownbit; Amask ^= ownbit; }
+        nocc += cd.cur ? -1 : 1;
+        if (!zero_after) {
+            const float sgn = cd.cur ? -1.f : 1.f;
+            // groups where the weight exceeds 2^-36 min S: what is skipped stays far below the FP32 resolution of S even
+            // when summed over every commit between two refreshes of S (at most 2^-36 x commits, in practice << 2^-30)
+            uint32_t m = __ballot_sync(0xffffffffu, lane < ept && !(wub < 1.4551915e-11f * Gw));
+#ifdef MP_DEBUG_CULL
+            if (lane == 0) atomicAdd(&g_cull_dbg[3], (unsigned long long)__popc(m));
+#endif
+            while (m) {                                   // warp-uniform
+                const int j = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const float4 tq = sT[tid + j * NT];
+                const float w = weight(tq, cd.k, cd.kx, cd.ky, cd.lawk);
+                const float a = j == kj ? 0.f : sgn * w;
+                const float s = tq.x + a, bb = s - tq.x;
+                const float e = (tq.x - (s - bb)) + (a - bb);
+                const float lo2 = tq.y + e;
+                float hi = s + lo2, lo = lo2 - (hi - s);
+                if (hi < 0.f) { hi = 0.f; lo = 0.f; }
+                *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
+                if (cd.cur) {
+                    // a removal lowers S: exact new minimum of the group (S_hi >= 0, so the bit pattern is order preserving);
+                    // after an addition the old minimum is still a lower bound
+                    const uint32_t mn = __reduce_min_sync(0xffffffffu, ((valid >> j) & 1u) ? (__float_as_uint(hi) & 0x7fffffffu) : 0x7f7fffffu);
+                    if (lane == j) Gw = __uint_as_float(mn);
+                }
+            }
+        } else {
+            for (int j = 0; j < ept; j++) {
+                const int s = g + j * TPT;
+                const double so = s < n ? src_offset(perm[s]) : 0.0;
+                const float hi = (float)so, lo = (float)(so - (double)hi);
+                *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
+            }
+            Gw = 0.f;
+        }
+        __syncwarp();
+    };
+
+    // ---- the scan.  Every trip evaluates TWO candidates against the current state: A = i and, speculatively, B = i + 1.
+    // If A is rejected (~2 of 3 flips) B's sum is already valid and the trip retires both; if A is accepted B is
+    // evaluated again on the next trip.  Decisions and state are exactly those of the one-at-a-time scan.
+    float wubA = ncand > 0 ? bound_of(0) : 0.f, wubB = ncand > 1 ? bound_of(1) : 0.f;
+    for (int i = 0; i < ncand;) {
+        if ((i / RC) != chunk) {                          // entered the next chunk: recycle the half we left
+            chunk = i / RC;
+            __syncthreads();
+            if (tid < 2 * RC) ring[((chunk + 1) & 1) * 2 * RC + tid] = pre;
+            __syncthreads();
+            pre = load_chunk(chunk + 2);
+        }
+        const bool haveB = i + 1 < ncand;
+        const Cand A = read_cand(i), B = read_cand(i + 1);
+        const bool zeroA = (nocc + (A.cur ? -1 : 1)) == 0, zeroB = (nocc + (B.cur ? -1 : 1)) == 0;
+        const bool ownA = (A.kslot % TPT) == g, ownB = (B.kslot % TPT) == g;
+        const int kjA = ownA ? A.kslot / TPT : 31, kjB = ownB ? B.kslot / TPT : 31;
+        const uint32_t bitA = ownA ? 1u << kjA : 0u, bitB = ownB ? 1u << kjB : 0u;
+        // groups that can feel the candidate at the FP32 resolution of S_hi (2^-26 min S, with a margin for the drift of
+        // min S in groups whose commits were skipped)
+        const uint32_t actA = __ballot_sync(0xffffffffu, lane < ept && !(wubA < 1.4886e-8f * Gw));
+        const uint32_t actB = __ballot_sync(0xffffffffu, lane < ept && !(wubB < 1.4886e-8f * Gw));
+#ifdef MP_DEBUG_CULL
+        if (lane == 0) { atomicAdd(&g_cull_dbg[0], 1ull); atomicAdd(&g_cull_dbg[1], (unsigned long long)(__popc(actA) + __popc(actB))); atomicAdd(&g_cull_dbg[2], (unsigned long long)(2 * ept)); }
+#endif
+        float2 acc = make_float2(0.f, 0.f);
+        if (!zeroA) acc.x = evaluate(A, actA, ownA, kjA, Amask & ~bitA, Bmask);
+        if (haveB && !zeroB) acc.y = evaluate(B, actB, ownB, kjB, Amask & ~bitB, Bmask);
+        // bounds of the two candidates after these: independent of this trip's outcome, they complete under the reduction
+        const float wubC = bound_of(i + 2), wubD = bound_of(i + 3);
+        const float2 tot = all_reduce(0, acc);
+
+        float totA = tot.x;
+        if (zeroA || isnan(totA)) totA = all_reduce(1, make_float2(evaluate_careful(A, zeroA, ownA, kjA, Amask & ~bitA, Bmask), 0.f)).x;
+        if (A.thr < 0.6931471805599453f * totA) {
+            commit(A, wubA, zeroA, ownA, kjA, bitA);
+            i += 1; wubA = wubB; wubB = wubC;
+            continue;
+        }
+        if (haveB) {
+            float totB = tot.y;
+            if (zeroB || isnan(totB)) totB = all_reduce(1, make_float2(evaluate_careful(B, zeroB, ownB, kjB, Amask & ~bitB, Bmask), 0.f)).x;
+            if (B.thr < 0.6931471805599453f * totB) commit(B, wubB, zeroB, ownB, kjB, bitB);
+        }
+        i += 2; wubA = wubC; wubB = wubD;
+    }
+    for (int j = 0; j < ept; j++) {
+        const int s = g + j * TPT;
+        if (s < n) {
+            const int q = perm[s];
+            const float4 tq = sT[tid + j * NT];
+            St[q] = fmax(((double)tq.x + (double)tq.y) - src_offset(q), 0.0);
+            yt[q] = (uint8_t)((ybits >> j) & 1u);
+        }
+    }
+    if (CS > 1) cluster_barrier();
+}
+
+}  // namespace mp
+
+#if defined(MP_FAST_GEOM) && defined(MP_FAST_HAS_POSITIONS)
+namespace mp {
+template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept)
+{
+    constexpr int NT = TPT / CS;
+    const size_t smem = (size_t)ept * NT * 16 + 2 * 32 * 32;   // targets + the two-chunk record ring
+    REQUIRE(smem <= 227 * 1024 && ept <= 31, MP_ERR_UNSUPPORTED, "n_patches too large for the fast y sweep");
+    auto kern = k_sweep_y_cull<MP_FAST_GEOM, CS, TPT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const int ntask_all = h->cfg.n_chains * (h->cfg.n_years - 1);
+    const int ntask = (ntask_all - h->task_first + h->task_stride - 1) / h->task_stride;
+    if (ntask <= 0) return MP_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ntask * CS));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const int *)h->d_perm, (const mp_params *)h->d_par,
+                          (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
+                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, h->task_first, h->task_stride));
+    return MP_OK;
+}
+// culled variants exist for 512 threads per task (N up to 15,872) and the large-landscape geometries
+static int launch_cull_any(mp_engine *h, int cs, int tpt)
+{
+    const int ept = (h->cfg.n_patches + tpt - 1) / tpt;
+    if (tpt == 512) switch (cs) {
+        case 1: return launch_cull<1, 512>(h, ept);
+        case 2: return launch_cull<2, 512>(h, ept);
+        case 4: return launch_cull<4, 512>(h, ept);
+        default: return launch_cull<8, 512>(h, ept);
+    }
+    if (tpt == 2048) return launch_cull<8, 2048>(h, ept);
+    if (tpt == 4096) return cs == 16 ? launch_cull<16, 4096>(h, ept) : launch_cull<8, 4096>(h, ept);
+    if (tpt == 8192) return cs == 16 ? launch_cull<16, 8192>(h, ept) : launch_cull<8, 8192>(h, ept);
+    return MP_ERR_UNSUPPORTED;
+}
+}  // namespace mp
+#endif

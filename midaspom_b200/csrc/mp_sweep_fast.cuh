@@ -27,7 +27,7 @@
 
 namespace mp {
 
-struct CandRec { uint32_t kinfo; float kx, ky, lawk, thr; uint32_t pad[3]; };   // 32 bytes
+struct CandRec { uint32_t kinfo; float kx, ky, lawk, thr; uint32_t pad[3]; };   // 32 bytes; pad[0] = Morton slot of the patch
 
 // ------------------------------------------------------------------ cluster / DSMEM primitives
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -55,19 +55,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 {
+    // the suspend-time hint lets the hardware park the warp until the phase completes instead of re-issuing the poll
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity), "r"(20000u) : "memory");
 }
 // remote 4-byte store that completes 4 tx bytes on the destination CTA's mbarrier
 __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar)
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                  ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float2 v, uint32_t remote_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(remote_mbar) : "memory");
 }
 __device__ __forceinline__ float warp_sum_f(float v)
 {
@@ -81,7 +87,8 @@ __device__ __forceinline__ float warp_sum_f(float v)
 static __global__ void __launch_bounds__(1024)
 k_build_candidates(uint64_t seed, int chain_offset, uint32_t sweep, Landscape<float> ls, const float *__restrict__ aw,
                    const uint8_t *__restrict__ z, const uint8_t *__restrict__ y, CandRec *__restrict__ rec,
-                   int *__restrict__ count /* [task][2]: candidates, occupied */, int T, int coords, int task_first, int task_stride)
+                   int *__restrict__ count /* [task][2]: candidates, occupied */, int T, int coords, int task_first, int task_stride,
+                   const int *__restrict__ inv /* patch -> Morton slot */)
 {
     __shared__ int s_cnt[1024], s_occ[32];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x;
@@ -109,7 +116,7 @@ k_build_candidates(uint64_t seed, int chain_offset, uint32_t sweep, Landscape<fl
         r.kx = coords ? ls.px[q] : 0.f; r.ky = coords ? ls.py[q] : 0.f;
         r.lawk = aw[(size_t)c * n + q];                 // FP32 engines keep log2 A^b (area_pre<float>)
         r.thr = (float)logit_u(rng(seed, (uint32_t)(chain_offset + c), sweep, RK_Y, (uint32_t)q, (uint32_t)t).x);
-        r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        r.pad[0] = (uint32_t)inv[q]; r.pad[1] = r.pad[2] = 0;
         out[off++] = r;
     }
     if (tid == 1023) count[2 * task] = s_cnt[1023];
