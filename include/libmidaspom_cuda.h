@@ -95,6 +95,9 @@ int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area /* 
 int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, const double *area);
 int mp_set_landscape_dense(mp_engine *h, const double *dist /* N*N, [source][target] */, const double *area);
 int mp_set_source_units(mp_engine *h, const double *src_unit /* N or NULL => k+1 */);
+/* Order in which the y scan visits the patches of a year (slot -> patch): the Morton order of planar
+ * coordinates, index order for linear and dense landscapes (oracle: spom_scan_order). */
+int mp_get_scan_order(mp_engine *h, int32_t *order /* N */);
 
 /* ---- data ---- */
 int mp_set_observations(mp_engine *h, const int8_t *obs /* T*N, -1/0/1 */);

@@ -102,7 +102,7 @@ template <typename R, int GEOM> static int launch_sweep_y_g(mp_engine *h)
     const int nthr = (int)std::min<size_t>(NT, ((nN(h) + 31) / 32) * 32);
     kern<<<h->cfg.n_chains * (h->cfg.n_years - 1), nthr, smem, h->stream>>>(
         sampler_dev(h), h->sweep, view<R>(h), h->d_par, (const R *)h->d_aw[0], h->have_era ? h->d_era : nullptr, h->d_z,
-        h->d_y, h->d_S[0], h->cfg.n_years);
+        h->d_y, h->d_S[0], h->cfg.n_years, (const int *)h->d_perm);
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -132,7 +132,7 @@ static int launch_sweep_y_fast(mp_engine *h)
         k_build_candidates<<<ntask, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
                                                            (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
                                                            h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS,
-                                                           h->task_first, h->task_stride, h->d_inv);
+                                                           h->task_first, h->task_stride, h->d_perm);
         CK(cudaGetLastError());
     }
     Timed tm(h, MP_K_SWEEP_Y);
@@ -475,6 +475,15 @@ static int set_patch_order(mp_engine *h, const double *x, const double *y)
     for (size_t s = 0; s < N; s++) inv[perm[s]] = (int)s;
     CK(cudaMemcpy(h->d_perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_inv, inv.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    return MP_OK;
+}
+int mp_get_scan_order(mp_engine *h, int32_t *order)
+{
+    if (!h || !order) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(h->have_landscape, MP_ERR_STATE, "set the landscape first");
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
+    CK(cudaMemcpy(order, h->d_perm, nN(h) * sizeof(int), cudaMemcpyDeviceToHost));
     return MP_OK;
 }
 int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)

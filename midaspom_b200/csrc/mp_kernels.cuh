@@ -561,7 +561,8 @@ __global__ void k_flip_delta(Landscape<R> ls, const mp_params *__restrict__ par,
 template <typename R, int GEOM, int NT>
 __global__ void __launch_bounds__(NT, 1)
 k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
-          const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S, int T)
+          const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S, int T,
+          const int *__restrict__ order /* visiting order of the scan: slot -> patch (oracle: spom_scan_order) */)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, nthr = blockDim.x;
@@ -593,7 +594,8 @@ k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__res
 
     const uint32_t gchain = (uint32_t)(sd.chain_offset + c);
     int it = 0;
-    for (int k = 0; k < n; k++) {
+    for (int sl = 0; sl < n; sl++) {
+        const int k = order[sl];
         const int fk = sF[k];
         if ((fk & 6) != 6) continue;                    // candidate iff z_t[k] = z_t+1[k] = 1
         const int par_i = it & 1; it++;

@@ -23,6 +23,15 @@
 #pragma once
 #include "mp_sweep_fast.cuh"
 
+// candidates evaluated per trip (1 + speculative ones), measured: cfg3 (512 threads per task) 10.0 / 10.4 / 11.1 ms for 2 / 3 / 4,
+// cfg5t (8192 threads per task, exchange-latency bound) 43.4 / 39.3 / 38.8 ms
+#ifndef MP_CULL_SPEC
+#define MP_CULL_SPEC 2
+#endif
+#ifndef MP_CULL_SPEC_LARGE
+#define MP_CULL_SPEC_LARGE 4
+#endif
+
 namespace mp {
 
 #ifdef MP_DEBUG_CULL
@@ -36,12 +45,12 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
                const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, int task_first, int task_stride)
 {
     static_assert(GEOM != MP_GEOM_DENSE, "culling needs positions");
-    constexpr int NT = TPT / CS, NW = NT / 32;
+    constexpr int NT = TPT / CS, NW = NT / 32, SP = TPT > 1024 ? MP_CULL_SPEC_LARGE : MP_CULL_SPEC;
     constexpr bool HIER = TPT / 32 > 32;
     constexpr int NSLOT = HIER ? CS : TPT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) float2 red[2][2][32];
-    __shared__ __align__(8) float2 wred[HIER ? 2 : 1][2][32];
+    __shared__ __align__(16) float4 red[2][2][32];
+    __shared__ __align__(16) float4 wred[HIER ? 2 : 1][2][32];
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
@@ -114,33 +123,40 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     const CandRec *recs = rec + (size_t)task * n;
     uint32_t uses[2] = { 0u, 0u };
 
-    // sum of a pair of per-thread values over the task's TPT threads (warp shuffles, then st.async of the warp or
-    // CTA partial to every CTA of the cluster, completion counted on the destination's mbarrier)
-    auto all_reduce = [&](int round, float2 v) -> float2 {
+    // sums of SP per-thread values over the task's TPT threads (warp shuffles, then one st.async of the warp or CTA
+    // partials to every CTA of the cluster, completion counted on the destination's mbarrier)
+    auto all_reduce = [&](int round, float (&v)[SP]) {
         const uint32_t u = uses[round]++;
         const int p = u & 1;
-        v.x = warp_sum_f(v.x); v.y = warp_sum_f(v.y);
+        auto pack = [&]() { return make_float4(v[0], SP > 1 ? v[1 % SP] : 0.f, SP > 2 ? v[2 % SP] : 0.f, SP > 3 ? v[3 % SP] : 0.f); };
+        auto unpack_sum = [&](const float4 &t) {
+            v[0] = warp_sum_f(t.x);
+            if (SP > 1) v[1 % SP] = warp_sum_f(t.y);
+            if (SP > 2) v[2 % SP] = warp_sum_f(t.z);
+            if (SP > 3) v[3 % SP] = warp_sum_f(t.w);
+        };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < SP; c++) v[c] = warp_sum_f(v[c]);
         if (HIER) {
-            if (lane == 0) wred[round][p][wid] = v;
+            if (lane == 0) wred[round][p][wid] = pack();
             __syncthreads();
-            const float2 t = lane < NW ? wred[round][p][lane] : make_float2(0.f, 0.f);
-            v.x = warp_sum_f(t.x); v.y = warp_sum_f(t.y);
+            unpack_sum(lane < NW ? wred[round][p][lane] : zero4);
         }
         if (CS > 1) {
             const uint32_t boff = (uint32_t)(round * 2 + p) * 8u;
             const uint32_t slot = HIER ? rank : rank * NW + wid;
-            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)slot) * 8u;
-            if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 8);
-            if (lane < CS && (!HIER || wid == 0)) st_async_f32x2(red_remote + roff, v, bar_remote + boff);
+            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)slot) * 16u;
+            if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 16);
+            if (lane < CS && (!HIER || wid == 0)) st_async_f32x4(red_remote + roff, pack(), bar_remote + boff);
             mbar_wait(bar_local + boff, (u >> 1) & 1u);
-            const float2 t = lane < NSLOT ? red[round][p][lane] : make_float2(0.f, 0.f);
-            return make_float2(warp_sum_f(t.x), warp_sum_f(t.y));
+            unpack_sum(lane < NSLOT ? red[round][p][lane] : zero4);
+            return;
         }
-        if (HIER) return v;
-        if (lane == 0) red[round][p][wid] = v;
+        if (HIER) return;
+        if (lane == 0) red[round][p][wid] = pack();
         __syncthreads();
-        const float2 t = lane < NSLOT ? red[round][p][lane] : make_float2(0.f, 0.f);
-        return make_float2(warp_sum_f(t.x), warp_sum_f(t.y));
+        unpack_sum(lane < NSLOT ? red[round][p][lane] : zero4);
     };
     // weight of (candidate k, target in slot data tq)
     auto weight = [&](const float4 &tq, int k, float kx, float ky, float lawk) -> float {
@@ -191,39 +207,6 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     auto bound_of = [&](int i) -> float {
         const float4 a = ring[(i & (2 * RC - 1)) * 2];
         return group_bound((int)(__float_as_uint(a.x) & 0x7fffffffu), a.y, a.z, a.w);
-    };
-    // lg2 of the likelihood ratio of flipping candidate cd, this thread's share (evaluated groups only)
-    auto evaluate = [&](const Cand &cd, uint32_t active, bool own, int kj, uint32_t Ae, uint32_t Be) -> float {
-        const float sgn = cd.cur ? -1.f : 1.f;
-        float acc2 = 0.f;
-        uint32_t m = active;
-        // B independent (sqrt, ex2, 2 x FFMA.SAT) chains per trip
-        auto batch = [&](auto BB) {
-            constexpr int B = decltype(BB)::value;
-            float pn = 1.f, pd = 1.f;
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                const int j = __ffs((int)m) - 1;
-                m &= m - 1u;
-                const float4 tq = sT[tid + j * NT];
-                const float w = weight(tq, cd.k, cd.kx, cd.ky, cd.lawk);
-                // class A (z'=1): sat(cK S); class B (z'=0): sat(1 - cK S); neither: 1 -- as one FFMA.SAT with selected constants
-                const bool a = (Ae >> j) & 1u, b = (Be >> j) & 1u;
-                const float mul = a ? cK : (b ? -cK : 0.f), add = a ? 0.f : 1.f;
-                pn *= __saturatef(fmaf(mul, fmaf(sgn, w, tq.x) + tq.y, add));
-                pd *= __saturatef(fmaf(mul, tq.x + tq.y, add));
-            }
-            acc2 += Num<float>::lg2(pn) - Num<float>::lg2(pd);
-        };
-        while (m) {                                       // warp-uniform
-            const int left = __popc(m);
-            if (left >= 4) batch(std::integral_constant<int, 4>());
-            else if (left == 3) batch(std::integral_constant<int, 3>());
-            else if (left == 2) batch(std::integral_constant<int, 2>());
-            else batch(std::integral_constant<int, 1>());
-        }
-        if (own) acc2 += own_term(kj, cd.cur);
-        return acc2;
     };
     // cell-by-cell evaluation with the (-inf) - (-inf) := 0 convention (impossible current state, removal of the last occupied patch)
     auto evaluate_careful = [&](const Cand &cd, bool zero_after, bool own, int kj, uint32_t Ae, uint32_t Be) -> float {
@@ -283,10 +266,15 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
         __syncwarp();
     };
 
-    // ---- the scan.  Every trip evaluates TWO candidates against the current state: A = i and, speculatively, B = i + 1.
-    // If A is rejected (~2 of 3 flips) B's sum is already valid and the trip retires both; if A is accepted B is
-    // evaluated again on the next trip.  Decisions and state are exactly those of the one-at-a-time scan.
-    float wubA = ncand > 0 ? bound_of(0) : 0.f, wubB = ncand > 1 ? bound_of(1) : 0.f;
+    // ---- the scan.  Every trip evaluates SP consecutive candidates i .. i+SP-1 against the CURRENT state, in one pass over
+    // the union of their active groups (candidates come in Morton order, so the sets nearly coincide; a slot that only some
+    // of them feel contributes an exact factor ratio of 1 to the others) and one exchange of SP sums.  They are then
+    // decided in order: candidate c's sum is valid as long as all before it were rejected (2 of 3 flips are), the first
+    // accepted one is committed and the rest of the window is evaluated again on the next trip.  Decisions and state
+    // are exactly those of the one-at-a-time scan.
+    float wub[SP];
+#pragma unroll
+    for (int c = 0; c < SP; c++) wub[c] = c < ncand ? bound_of(c) : 0.f;
     for (int i = 0; i < ncand;) {
         if ((i / RC) != chunk) {                          // entered the next chunk: recycle the half we left
             chunk = i / RC;
@@ -295,39 +283,88 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             __syncthreads();
             pre = load_chunk(chunk + 2);
         }
-        const bool haveB = i + 1 < ncand;
-        const Cand A = read_cand(i), B = read_cand(i + 1);
-        const bool zeroA = (nocc + (A.cur ? -1 : 1)) == 0, zeroB = (nocc + (B.cur ? -1 : 1)) == 0;
-        const bool ownA = (A.kslot % TPT) == g, ownB = (B.kslot % TPT) == g;
-        const int kjA = ownA ? A.kslot / TPT : 31, kjB = ownB ? B.kslot / TPT : 31;
-        const uint32_t bitA = ownA ? 1u << kjA : 0u, bitB = ownB ? 1u << kjB : 0u;
-        // groups that can feel the candidate at the FP32 resolution of S_hi (2^-26 min S, with a margin for the drift of
-        // min S in groups whose commits were skipped)
-        const uint32_t actA = __ballot_sync(0xffffffffu, lane < ept && !(wubA < 1.4886e-8f * Gw));
-        const uint32_t actB = __ballot_sync(0xffffffffu, lane < ept && !(wubB < 1.4886e-8f * Gw));
+        const int nc = min(SP, ncand - i);
+        float kx[SP], ky[SP], lawk[SP], sgn[SP], pn[SP], acc[SP];
+        int kj[SP], kk[SP];
+        bool zero[SP];
+        bool feel = false;
+#pragma unroll
+        for (int c = 0; c < SP; c++) {
+            const float4 a = ring[((i + c) & (2 * RC - 1)) * 2];
+            const int kslot = (int)__float_as_uint(ring[((i + c) & (2 * RC - 1)) * 2 + 1].y);
+            const uint32_t cur = __float_as_uint(a.x) >> 31;
+            kk[c] = (int)(__float_as_uint(a.x) & 0x7fffffffu);
+            kx[c] = a.y; ky[c] = a.z; lawk[c] = a.w; sgn[c] = cur ? -1.f : 1.f;
+            kj[c] = (kslot % TPT) == g ? kslot / TPT : 31;
+            zero[c] = (nocc + (cur ? -1 : 1)) == 0;
+            pn[c] = 1.f; acc[c] = 0.f;
+            // groups that can feel the candidate at the FP32 resolution of S_hi (2^-26 min S, with a margin for the drift
+            // of min S in groups whose commits were skipped)
+            feel = feel || (c < nc && !zero[c] && !(wub[c] < 1.4886e-8f * Gw));
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, lane < ept && feel);
 #ifdef MP_DEBUG_CULL
-        if (lane == 0) { atomicAdd(&g_cull_dbg[0], 1ull); atomicAdd(&g_cull_dbg[1], (unsigned long long)(__popc(actA) + __popc(actB))); atomicAdd(&g_cull_dbg[2], (unsigned long long)(2 * ept)); }
+        if (lane == 0) { atomicAdd(&g_cull_dbg[0], 1ull); atomicAdd(&g_cull_dbg[1], (unsigned long long)__popc(m)); atomicAdd(&g_cull_dbg[2], (unsigned long long)ept); }
 #endif
-        float2 acc = make_float2(0.f, 0.f);
-        if (!zeroA) acc.x = evaluate(A, actA, ownA, kjA, Amask & ~bitA, Bmask);
-        if (haveB && !zeroB) acc.y = evaluate(B, actB, ownB, kjB, Amask & ~bitB, Bmask);
-        // bounds of the two candidates after these: independent of this trip's outcome, they complete under the reduction
-        const float wubC = bound_of(i + 2), wubD = bound_of(i + 3);
-        const float2 tot = all_reduce(0, acc);
+        float pd = 1.f;
+        int cnt = 0;
+        while (m) {                                       // warp-uniform
+            const int j = __ffs((int)m) - 1;
+            m &= m - 1u;
+            const float4 tq = sT[tid + j * NT];
+            // class A (z'=1): sat(cK S); class B (z'=0): sat(1 - cK S); neither: 1 -- one FFMA.SAT with selected constants
+            const bool a = (Amask >> j) & 1u, b = (Bmask >> j) & 1u;
+            const float mul = a ? cK : (b ? -cK : 0.f), add = a ? 0.f : 1.f;
+            const float fd = __saturatef(fmaf(mul, tq.x + tq.y, add));
+            pd *= fd;
+#pragma unroll
+            for (int c = 0; c < SP; c++) {                // SP independent (sqrt, ex2, FFMA.SAT) chains
+                const float w = weight(tq, kk[c], kx[c], ky[c], lawk[c]);
+                const float fn = __saturatef(fmaf(mul, fmaf(sgn[c], w, tq.x) + tq.y, add));
+                pn[c] *= j == kj[c] ? fd : fn;            // the candidate's own cell is handled by own_term
+            }
+            if (++cnt == 4 || m == 0u) {                  // products of at most 4 factors stay far from underflow
+                const float lpd = Num<float>::lg2(pd);
+#pragma unroll
+                for (int c = 0; c < SP; c++) { acc[c] += Num<float>::lg2(pn[c]) - lpd; pn[c] = 1.f; }
+                pd = 1.f; cnt = 0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < SP; c++) if (kj[c] != 31) acc[c] += own_term(kj[c], sgn[c] < 0.f);
+        // bounds of the SP candidates after this window: independent of this trip's outcome, they complete under the reduction
+        float nxt[SP];
+#pragma unroll
+        for (int c = 0; c < SP; c++) nxt[c] = bound_of(i + SP + c);
+        all_reduce(0, acc);
 
-        float totA = tot.x;
-        if (zeroA || isnan(totA)) totA = all_reduce(1, make_float2(evaluate_careful(A, zeroA, ownA, kjA, Amask & ~bitA, Bmask), 0.f)).x;
-        if (A.thr < 0.6931471805599453f * totA) {
-            commit(A, wubA, zeroA, ownA, kjA, bitA);
-            i += 1; wubA = wubB; wubB = wubC;
-            continue;
+        int adv = nc;
+#pragma unroll
+        for (int c = 0; c < SP; c++) {
+            if (c < adv) {                                // still undecided and inside the list (adv shrinks on the first accept)
+                const Cand cd = read_cand(i + c);
+                const bool own = kj[c] != 31;
+                const uint32_t bit = own ? 1u << kj[c] : 0u;
+                float tot = acc[c];
+                if (zero[c] || isnan(tot)) {
+                    float v[SP];
+#pragma unroll
+                    for (int d = 0; d < SP; d++) v[d] = 0.f;
+                    v[0] = evaluate_careful(cd, zero[c], own, kj[c], Amask & ~bit, Bmask);
+                    all_reduce(1, v);
+                    tot = v[0];
+                }
+                if (cd.thr < 0.6931471805599453f * tot) { commit(cd, wub[c], zero[c], own, kj[c], bit); adv = c + 1; }
+            }
         }
-        if (haveB) {
-            float totB = tot.y;
-            if (zeroB || isnan(totB)) totB = all_reduce(1, make_float2(evaluate_careful(B, zeroB, ownB, kjB, Amask & ~bitB, Bmask), 0.f)).x;
-            if (B.thr < 0.6931471805599453f * totB) commit(B, wubB, zeroB, ownB, kjB, bitB);
-        }
-        i += 2; wubA = wubC; wubB = wubD;
+        i += adv;
+        // slide the window of bounds by adv
+#pragma unroll
+        for (int aa = 1; aa <= SP; aa++)
+            if (adv == aa) {
+#pragma unroll
+                for (int c = 0; c < SP; c++) wub[c] = aa + c < SP ? wub[(aa + c) % SP] : nxt[(aa + c - SP) % SP];
+            }
     }
     for (int j = 0; j < ept; j++) {
         const int s = g + j * TPT;

@@ -29,6 +29,7 @@ ABI_SYMBOLS = (
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
     "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
+    "mp_get_scan_order",
 )
 
 
@@ -93,6 +94,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_set_landscape_coords.argtypes = [vp, dp, dp, dp]
     L.mp_set_landscape_dense.argtypes = [vp, dp, dp]
     L.mp_set_source_units.argtypes = [vp, dp]
+    L.mp_get_scan_order.argtypes = [vp, C.POINTER(C.c_int32)]
     L.mp_set_observations.argtypes = [vp, i8p]
     L.mp_set_era.argtypes = [vp, u8p]
     L.mp_set_params.argtypes = [vp, pp]; L.mp_get_params.argtypes = [vp, pp]
@@ -195,6 +197,12 @@ class Engine:
     def set_source_units(self, src_unit=None):
         src_unit = self._f64(src_unit, (self.N,))
         self._ck(self.lib.mp_set_source_units(self.h, _p(src_unit, _dp)), "mp_set_source_units")
+
+    def scan_order(self) -> np.ndarray:
+        """Visiting order of the y scan (slot -> patch); Morton order for planar landscapes."""
+        out = np.zeros(self.N, dtype=np.int32)
+        self._ck(self.lib.mp_get_scan_order(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))), "mp_get_scan_order")
+        return out
 
     def set_observations(self, obs):
         obs = np.ascontiguousarray(obs, dtype=np.int8)

@@ -54,6 +54,51 @@ static void box_muller(uint32_t x0, uint32_t x1, double *n1, double *n2)
     *n1 = r * cos(th); *n2 = r * sin(th);
 }
 
+/* ------------------------------------------------------------------ scan order */
+/* Order in which the systematic y scan visits the patches of a year.  Any fixed order is a valid
+ * Gibbs scan; planar landscapes use the Z-order (Morton) curve of the coordinates, quantised to
+ * 16 bits per axis over the bounding square, ties in index order, so that consecutive visits are
+ * spatial neighbours (the CUDA engine exploits that; both sides must visit in the same order for
+ * the draw-by-draw twin tests).  Linear and dense landscapes are visited in index order. */
+static uint32_t morton_spread16(uint32_t v)
+{
+    v &= 0xffffu; v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+typedef struct { uint32_t code; int32_t idx; } scan_key;
+static int scan_key_cmp(const void *a, const void *b)
+{
+    const scan_key *x = a, *y = b;
+    if (x->code != y->code) return x->code < y->code ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+void spom_scan_order(const spom_model *m, int32_t *order)
+{
+    const int n = m->n;
+    if (m->geom != SPOM_GEOM_COORDS || n == 0) { for (int k = 0; k < n; k++) order[k] = k; return; }
+    double x0 = m->px[0], x1 = m->px[0], y0 = m->py[0], y1 = m->py[0];
+    for (int k = 1; k < n; k++) {
+        if (m->px[k] < x0) x0 = m->px[k];
+        if (m->px[k] > x1) x1 = m->px[k];
+        if (m->py[k] < y0) y0 = m->py[k];
+        if (m->py[k] > y1) y1 = m->py[k];
+    }
+    double span = x1 - x0 > y1 - y0 ? x1 - x0 : y1 - y0;
+    if (!(span > 1e-300)) span = 1e-300;
+    scan_key *key = malloc((size_t)n * sizeof *key);
+    for (int k = 0; k < n; k++) {
+        double fx = (m->px[k] - x0) / span * 65535.0, fy = (m->py[k] - y0) / span * 65535.0;
+        if (fx > 65535.0) fx = 65535.0;
+        if (fy > 65535.0) fy = 65535.0;
+        key[k].code = morton_spread16((uint32_t)fx) | (morton_spread16((uint32_t)fy) << 1);
+        key[k].idx = k;
+    }
+    qsort(key, (size_t)n, sizeof *key, scan_key_cmp);
+    for (int s = 0; s < n; s++) order[s] = key[s].idx;
+    free(key);
+}
+
 /* ------------------------------------------------------------------ model pieces */
 static inline double pair_distance(const spom_model *m, int a, int b)
 {
@@ -587,6 +632,8 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
         const double t_y0 = now_s();
         double *L = malloc((size_t)n * sizeof(double)), *sa = malloc((size_t)n * sizeof(double)),
                *la = malloc((size_t)n * sizeof(double));
+        int32_t *order = malloc((size_t)n * sizeof(int32_t));
+        spom_scan_order(m, order);
         for (int t = 0; t + 1 < T; t++) {
             uint8_t *y_t = y + (size_t)t * n;
             const uint8_t *z_t = z + (size_t)t * n, *z_n = z + (size_t)(t + 1) * n;
@@ -599,7 +646,8 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
                 L[k] = y_t[k] ? 0.0 : log_col(z_n[k], col_prob(par, pre, S_t[k], g));
             }
             int64_t vis_t = 0;
-            for (int k = 0; k < n; k++) {
+            for (int sl = 0; sl < n; sl++) {
+                const int k = order[sl];
                 if (!(z_t[k] && z_n[k])) continue;
                 if (y_flip_limit >= 0 && vis_t >= y_flip_limit) break;
                 vis_t++;
@@ -618,7 +666,7 @@ int64_t spom_sweep(const spom_model *m, const spom_sampler_cfg *cfg, uint64_t se
             }
             visited += vis_t;
         }
-        free(L); free(sa); free(la);
+        free(L); free(sa); free(la); free(order);
         t_yscan = now_s() - t_y0;
     }
     /* C: random-walk MH on e from the sufficient counts */

@@ -74,6 +74,9 @@ void   spom_rng(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t kind, ui
                 uint32_t out[4]);
 double spom_u01(uint32_t x);
 
+/* ---- visiting order of the y scan (Morton order of planar coordinates, else index order) ---- */
+void   spom_scan_order(const spom_model *m, int32_t *order);
+
 /* ---- likelihood pieces ---- */
 double spom_weight(const spom_model *m, double alpha, double b, int target, int source);
 void   spom_connectivity(const spom_model *m, double alpha, double b, const uint8_t *y_row, double *S_row);

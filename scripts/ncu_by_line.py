@@ -29,3 +29,17 @@ for (f, l), v in sorted(inst.items(), key=lambda x: -x[1])[:45]:
         except Exception: src[f] = None
     text = src[f][l - 1].strip()[:90] if src[f] else ''
     print(f"{100*v/ti:5.1f}% inst {100*samp[(f,l)]/ts:5.1f}% samp  {f}:{l}  {text}")
+
+if len(sys.argv) > 4:      # regions: name:file:lo-hi,...
+    print()
+    regs = []
+    for spec in sys.argv[4].split(','):
+        name, f, rng = spec.split(':'); lo, hi = map(int, rng.split('-')); regs.append((name, f, lo, hi))
+    agg = collections.Counter(); aggs = collections.Counter()
+    for (k, v) in inst.items():
+        if k is None: continue
+        f, l = k
+        for name, rf, lo, hi in regs:
+            if f == rf and lo <= l <= hi: agg[name] += v; aggs[name] += samp[k]; break
+        else: agg['other'] += v; aggs['other'] += samp[k]
+    for name, v in agg.most_common(): print(f"{100*v/ti:5.1f}% inst {100*aggs[name]/ts:5.1f}% samp  {name}")
