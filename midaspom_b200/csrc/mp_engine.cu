@@ -47,10 +47,15 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     a.S[0] = h->d_S[0]; a.S[1] = h->d_S[1];
     a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords; a.set_base = set_base;
     a.k_lo = h->conn_lo; a.k_hi = h->conn_hi < 0 ? h->cfg.n_patches : h->conn_hi;
+    a.perm = h->d_perm; a.box32 = (const float4 *)h->d_tile_box;
     if (a.k_hi <= a.k_lo) return MP_OK;
     dim3 grid((a.k_hi - a.k_lo + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
     const int ny = a.ntrans;                          // year accumulators per target: next multiple of 4 (<= 32 per pass)
-#define MP_CONN(NYB) k_conn<R, GEOM, NYB><<<grid, CONN_TILE, 0, h->stream>>>(a)
+    // FP32 engines on landscapes with positions skip source tiles out of reach (see CONN_CULL_LOG2); FP64 never culls
+    constexpr bool CAN_CULL = sizeof(R) == 4 && GEOM != MP_GEOM_DENSE;
+    const bool cull = CAN_CULL && h->conn_cull && h->have_boxes;
+#define MP_CONN(NYB) do { if (cull) k_conn<R, GEOM, NYB, CAN_CULL><<<grid, CONN_TILE, 0, h->stream>>>(a); \
+                          else k_conn<R, GEOM, NYB, false><<<grid, CONN_TILE, 0, h->stream>>>(a); } while (0)
     if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
     else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);
 #undef MP_CONN
@@ -355,7 +360,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_ljac, h->d_perm, h->d_inv };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_ljac, h->d_perm, h->d_inv, h->d_tile_box };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -387,6 +392,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     mp_engine *h = new mp_engine();
     h->cfg = *cfg;
     if (const char *env = getenv("MP_FAST_CULL")) h->fast_cull = atoi(env) != 0;
+    if (const char *env = getenv("MP_CONN_CULL")) h->conn_cull = atoi(env) != 0;
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
@@ -418,6 +424,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) },
         { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_inv, N * sizeof(int) },
+        { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) },
     };
     for (auto &r : reqs) {
         if ((e = cudaMalloc(r.p, r.bytes)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -454,7 +461,7 @@ static int set_area(mp_engine *h, const double *area)
 }
 // Morton (Z-order) permutation of the patches: perm[slot] = patch, inv[patch] = slot.  Spatially adjacent
 // patches get adjacent slots, which is what makes the warp-level culling of k_sweep_y_cull effective.
-static int set_patch_order(mp_engine *h, const double *x, const double *y)
+static int set_patch_order(mp_engine *h, const double *x, const double *y, double spacing = 0.0)
 {
     const size_t N = nN(h);
     std::vector<int> perm(N), inv(N);
@@ -475,6 +482,20 @@ static int set_patch_order(mp_engine *h, const double *x, const double *y)
     for (size_t s = 0; s < N; s++) inv[perm[s]] = (int)s;
     CK(cudaMemcpy(h->d_perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_inv, inv.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    // bounding boxes of the groups of 32 consecutive slots (culled k_conn), in the FP32 coordinates the kernels use
+    const size_t ntile = (N + 31) / 32;
+    std::vector<float4> box(ntile);
+    h->have_boxes = (x && y) || spacing > 0.0;
+    for (size_t tI = 0; tI < ntile && h->have_boxes; tI++) {
+        float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
+        for (size_t sI = tI * 32; sI < std::min(N, (tI + 1) * 32); sI++) {
+            const int q = perm[sI];
+            const float fx = x ? (float)x[q] : (float)q * (float)spacing, fy = y ? (float)y[q] : 0.f;
+            bx0 = std::min(bx0, fx); bx1 = std::max(bx1, fx); by0 = std::min(by0, fy); by1 = std::max(by1, fy);
+        }
+        box[tI] = make_float4(bx0, bx1, by0, by1);
+    }
+    CK(cudaMemcpy(h->d_tile_box, box.data(), ntile * sizeof(float4), cudaMemcpyHostToDevice));
     return MP_OK;
 }
 int mp_get_scan_order(mp_engine *h, int32_t *order)
@@ -493,7 +514,7 @@ int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
     if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(spacing > 0.0, MP_ERR_ARG, "spacing must be positive");
     h->geom = MP_GEOM_LINEAR; h->spacing = spacing;
-    int rc = set_patch_order(h, nullptr, nullptr);      // a line is already in spatial order
+    int rc = set_patch_order(h, nullptr, nullptr, spacing);      // a line is already in spatial order
     if (rc != MP_OK) return rc;
     rc = set_area(h, area);
     if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }

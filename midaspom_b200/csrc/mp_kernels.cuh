@@ -62,10 +62,20 @@ template <typename R> struct ConnArgs {
     const uint32_t *ybits;
     int ntrans, nwords;
     int set_base;          // first parameter set of this launch (blockIdx.z counts from it)
-    int k_lo, k_hi;        // target patches [k_lo, k_hi) of this launch (patch sharding over GPUs; whole range otherwise)
+    int k_lo, k_hi;        // targets [k_lo, k_hi) of this launch (patch sharding over GPUs; whole range otherwise):
+                           // patch numbers, or scan-order slots for the culled variant
+    const int *perm;       // culled variant: scan-order slot -> patch (Morton order of planar landscapes)
+    const float4 *box32;   // culled variant: bounding box {xmin, xmax, ymin, ymax} of every group of 32 consecutive slots
 };
+// Culled variant (FP32 engines, landscapes with positions): targets and sources are taken in scan (Morton) order, so
+// groups of consecutive slots are spatially compact.  A tile of 128 sources is not even loaded when its box is so far
+// from the box of the CTA's 256 targets that exp(-alpha d) < 2^-28 for every pair, and each warp skips the 32-source
+// groups out of reach of its own 64 targets.  The skipped mass per target is at most 2^-28 sum_l A_l^b -- about 1e-7
+// of S on the benchmark landscapes (below FP32 resolution; the FP32 engine's tolerance is 1e-5).  The FP64 parity
+// engine never culls.
+constexpr float CONN_CULL_LOG2 = -28.f;
 
-template <typename R, int GEOM, int NYB>
+template <typename R, int GEOM, int NYB, bool CULL = false>
 __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
 {
     // Each thread owns CONN_TGT targets (k, k + 128, ...) and NYB year accumulators per target.
@@ -75,19 +85,41 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
     // fed by broadcast LDS.128; the y01 loads are shared by the CONN_TGT targets of the thread.
     __shared__ R sx[CONN_TILE], sy[CONN_TILE], saw[CONN_TILE];
     __shared__ uint32_t sbits[CONN_TILE];
+    __shared__ int sl[CULL ? CONN_TILE : 1];                          // culled variant: patch number of the tile's sources
     __shared__ __align__(16) double sy01[CONN_TILE][NYB];
     const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z + a.set_base, tid = threadIdx.x;
-    const int kbase = a.k_lo + blockIdx.x * CONN_TILE * CONN_TGT + tid;
+    // first target of the thread: patch kbase, then kbase + 128 (coalesced stores); in the culled variant scan-order
+    // slots kbase, kbase + 32, so that a warp owns 64 consecutive slots -- one spatially compact group
+    const int kstep = CULL ? 32 : CONN_TILE;
+    const int kbase = a.k_lo + blockIdx.x * CONN_TILE * CONN_TGT + (CULL ? (tid >> 5) * 32 * CONN_TGT + (tid & 31) : tid);
     const mp_params *parp = set ? a.par[1] : a.par[0];
     const R apre = alpha_pre<R>(parp[c].alpha);
     const R *aw = (set ? a.aw[1] : a.aw[0]) + (size_t)c * n;
     double *Sout = (set ? a.S[1] : a.S[0]) + (size_t)c * a.ntrans * n;
     R tx[CONN_TGT], ty[CONN_TGT];
+    int kp[CONN_TGT];                                                 // patch number of the thread's targets (-1: none)
 #pragma unroll
     for (int g = 0; g < CONN_TGT; g++) {
-        const int k = kbase + g * CONN_TILE;
+        const int k = kbase + g * kstep;
+        kp[g] = k < a.k_hi ? (CULL ? a.perm[k] : k) : -1;
         tx[g] = 0; ty[g] = 0;
-        if (GEOM == MP_GEOM_COORDS && k < a.k_hi) { tx[g] = a.ls.px[k]; ty[g] = a.ls.py[k]; }
+        if (GEOM == MP_GEOM_COORDS && kp[g] >= 0) { tx[g] = a.ls.px[kp[g]]; ty[g] = a.ls.py[kp[g]]; }
+    }
+    // boxes {xmin, xmax, ymin, ymax} of the CTA's targets and of the warp's targets (unions of 32-slot group boxes)
+    float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f), wbox = tbox;
+    auto box_union = [](const float4 &p, const float4 &q) { return make_float4(fminf(p.x, q.x), fmaxf(p.y, q.y), fminf(p.z, q.z), fmaxf(p.w, q.w)); };
+    // log2 of the largest distance factor exp(-alpha d) between two boxes (apre = -alpha log2 e), with a rounding margin
+    auto reach_log2 = [&](const float4 &p, const float4 &q) {
+        const float dx = fmaxf(0.f, fmaxf(q.x - p.y, p.x - q.y)), dy = fmaxf(0.f, fmaxf(q.z - p.w, p.z - q.w));
+        return (float)apre * (0.9999f * sqrtf(dx * dx + dy * dy));
+    };
+    if (CULL) {
+        const int g0 = (a.k_lo + blockIdx.x * CONN_TILE * CONN_TGT) / 32, gend = (a.k_hi + 31) / 32;
+        tbox = a.box32[g0];
+        for (int i = 1; i < CONN_TILE * CONN_TGT / 32; i++) if (g0 + i < gend) tbox = box_union(tbox, a.box32[g0 + i]);
+        const int w0 = g0 + (tid >> 5) * CONN_TGT;
+        wbox = a.box32[min(w0, gend - 1)];
+        for (int i = 1; i < CONN_TGT; i++) if (w0 + i < gend) wbox = box_union(wbox, a.box32[w0 + i]);
     }
     for (int w = 0; w < a.nwords; w++) {
         const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
@@ -96,47 +128,63 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
         for (int g = 0; g < CONN_TGT; g++)
 #pragma unroll
             for (int t = 0; t < NYB; t++) acc[g][t] = 0.0;
+        // one source of the tile against the thread's targets
+        auto source = [&](int l0, int j) {
+            if (sbits[j] == 0) return;                                 // tile-uniform: source empty in every year
+            double wd[CONN_TGT];
+            const int lj = CULL ? sl[j] : l0 + j;
+#pragma unroll
+            for (int g = 0; g < CONN_TGT; g++) {
+                R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], kp[g], lj, tx[g], ty[g], sx[j], sy[j]);
+                if (lj == kp[g]) wgt = 0;                               // l != k  (main_MIDASPOM.c:354)
+                wd[g] = (double)wgt;
+            }
+            const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
+#pragma unroll
+            for (int t2 = 0; t2 < NYB / 2; t2++) {
+                const double2 m = yb[t2];
+#pragma unroll
+                for (int g = 0; g < CONN_TGT; g++) {
+                    acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
+                    acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
+                }
+            }
+        };
         for (int l0 = 0; l0 < n; l0 += CONN_TILE) {
-            const int l = l0 + tid;
+            if (CULL) {                                                // CTA-uniform: is any (target, source) pair of the tile within reach?
+                float4 sb = a.box32[l0 / 32];
+                for (int i = 1; i < CONN_TILE / 32; i++) if (l0 + 32 * i < n) sb = box_union(sb, a.box32[l0 / 32 + i]);
+                if (reach_log2(tbox, sb) < CONN_CULL_LOG2) continue;
+            }
+            const int l = (CULL && l0 + tid < n) ? a.perm[l0 + tid] : l0 + tid;
             uint32_t bits = 0;
-            if (l < n) {
+            if (l0 + tid < n) {
                 if (GEOM == MP_GEOM_COORDS) { sx[tid] = a.ls.px[l]; sy[tid] = a.ls.py[l]; }
                 saw[tid] = aw[l]; bits = bw[l];
             }
+            if (CULL) sl[tid] = l;
             sbits[tid] = bits;
 #pragma unroll
             for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
             __syncthreads();
             if (kbase < a.k_hi) {
+                if (CULL) {
+                    for (int sub = 0; sub < CONN_TILE / 32; sub++) {   // warp-uniform: 32 sources against the warp's 64 targets
+                        if (l0 + 32 * sub >= n || reach_log2(wbox, a.box32[l0 / 32 + sub]) < CONN_CULL_LOG2) continue;
 #pragma unroll 2
-                for (int j = 0; j < CONN_TILE; j++) {
-                    if (sbits[j] == 0) continue;                       // tile-uniform: source empty in every year
-                    double wd[CONN_TGT];
-#pragma unroll
-                    for (int g = 0; g < CONN_TGT; g++) {
-                        const int k = kbase + g * CONN_TILE;
-                        R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], k, l0 + j, tx[g], ty[g], sx[j], sy[j]);
-                        if (l0 + j == k) wgt = 0;                       // l != k  (main_MIDASPOM.c:354)
-                        wd[g] = (double)wgt;
+                        for (int j = 32 * sub; j < 32 * sub + 32; j++) source(l0, j);
                     }
-                    const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
-#pragma unroll
-                    for (int t2 = 0; t2 < NYB / 2; t2++) {
-                        const double2 m = yb[t2];
-#pragma unroll
-                        for (int g = 0; g < CONN_TGT; g++) {
-                            acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
-                            acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
-                        }
-                    }
+                } else {
+#pragma unroll 2
+                    for (int j = 0; j < CONN_TILE; j++) source(l0, j);
                 }
             }
             __syncthreads();
         }
 #pragma unroll
         for (int g = 0; g < CONN_TGT; g++) {
-            const int k = kbase + g * CONN_TILE;
-            if (k < a.k_hi) {
+            const int k = kp[g];
+            if (k >= 0) {
 #pragma unroll
                 for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = acc[g][t];
             }

@@ -540,7 +540,9 @@ def test_full_size_properties_cfg3():
         zg, yg = eng.get_state()
         S_inc = eng.get_connectivity()
         S_new = eng.connectivity()
-        rel_close(S_inc, S_new, 1e-9, floor=1e-9)
+        # the FP32 engine's from-scratch S skips source groups with exp(-alpha d) < 2^-28 (k_conn, culled variant) while
+        # the rank-1 updates reach to 2^-36 of S: the two agree to ~1e-7, any lost update would show at >= 1e-4
+        rel_close(S_inc, S_new, 1e-6, floor=1e-9)
         obs = spec["obs"]
         for c in range(C):
             assert ((yg[c] <= zg[c][:-1]) & (yg[c] <= zg[c][1:])).all()
