@@ -235,24 +235,38 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
 #ifdef MP_DEBUG_CULL
             if (lane == 0) atomicAdd(&g_cull_dbg[3], (unsigned long long)__popc(m));
 #endif
-            while (m) {                                   // warp-uniform
-                const int j = __ffs((int)m) - 1;
-                m &= m - 1u;
-                const float4 tq = sT[tid + j * NT];
-                const float w = weight(tq, cd.k, cd.kx, cd.ky, cd.lawk);
-                const float a = j == kj ? 0.f : sgn * w;
-                const float s = tq.x + a, bb = s - tq.x;
-                const float e = (tq.x - (s - bb)) + (a - bb);
-                const float lo2 = tq.y + e;
-                float hi = s + lo2, lo = lo2 - (hi - s);
-                if (hi < 0.f) { hi = 0.f; lo = 0.f; }
-                *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
-                if (cd.cur) {
-                    // a removal lowers S: exact new minimum of the group (S_hi >= 0, so the bit pattern is order preserving);
-                    // after an addition the old minimum is still a lower bound
-                    const uint32_t mn = __reduce_min_sync(0xffffffffu, ((valid >> j) & 1u) ? (__float_as_uint(hi) & 0x7fffffffu) : 0x7f7fffffu);
-                    if (lane == j) Gw = __uint_as_float(mn);
+            // B slots per trip: B independent (LDS, sqrt, ex2, two-sum, STS) chains, the loop is latency bound otherwise
+            auto batch = [&](auto BB) {
+                constexpr int B = decltype(BB)::value;
+                int jj[B];
+                float4 tq[B];
+#pragma unroll
+                for (int u = 0; u < B; u++) { jj[u] = __ffs((int)m) - 1; m &= m - 1u; tq[u] = sT[tid + jj[u] * NT]; }
+#pragma unroll
+                for (int u = 0; u < B; u++) {
+                    const int j = jj[u];
+                    const float w = weight(tq[u], cd.k, cd.kx, cd.ky, cd.lawk);
+                    const float a = j == kj ? 0.f : sgn * w;
+                    const float s = tq[u].x + a, bb = s - tq[u].x;
+                    const float e = (tq[u].x - (s - bb)) + (a - bb);
+                    const float lo2 = tq[u].y + e;
+                    float hi = s + lo2, lo = lo2 - (hi - s);
+                    if (hi < 0.f) { hi = 0.f; lo = 0.f; }
+                    *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
+                    if (cd.cur) {
+                        // a removal lowers S: exact new minimum of the group (S_hi >= 0, so the bit pattern is order
+                        // preserving); after an addition the old minimum is still a lower bound
+                        const uint32_t mn = __reduce_min_sync(0xffffffffu, ((valid >> j) & 1u) ? (__float_as_uint(hi) & 0x7fffffffu) : 0x7f7fffffu);
+                        if (lane == j) Gw = __uint_as_float(mn);
+                    }
                 }
+            };
+            while (m) {                                   // warp-uniform
+                const int left = __popc(m);
+                if (left >= 4) batch(std::integral_constant<int, 4>());
+                else if (left == 3) batch(std::integral_constant<int, 3>());
+                else if (left == 2) batch(std::integral_constant<int, 2>());
+                else batch(std::integral_constant<int, 1>());
             }
         } else {
             for (int j = 0; j < ept; j++) {
@@ -308,22 +322,34 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
 #endif
         float pd = 1.f;
         int cnt = 0;
-        while (m) {                                       // warp-uniform
-            const int j = __ffs((int)m) - 1;
-            m &= m - 1u;
-            const float4 tq = sT[tid + j * NT];
-            // class A (z'=1): sat(cK S); class B (z'=0): sat(1 - cK S); neither: 1 -- one FFMA.SAT with selected constants
-            const bool a = (Amask >> j) & 1u, b = (Bmask >> j) & 1u;
-            const float mul = a ? cK : (b ? -cK : 0.f), add = a ? 0.f : 1.f;
-            const float fd = __saturatef(fmaf(mul, tq.x + tq.y, add));
-            pd *= fd;
+        // B slots x SP candidates per trip: B * SP independent (sqrt, ex2, FFMA.SAT) chains
+        auto slots = [&](auto BB) {
+            constexpr int B = decltype(BB)::value;
+            int jj[B];
+            float4 tq[B];
 #pragma unroll
-            for (int c = 0; c < SP; c++) {                // SP independent (sqrt, ex2, FFMA.SAT) chains
-                const float w = weight(tq, kk[c], kx[c], ky[c], lawk[c]);
-                const float fn = __saturatef(fmaf(mul, fmaf(sgn[c], w, tq.x) + tq.y, add));
-                pn[c] *= j == kj[c] ? fd : fn;            // the candidate's own cell is handled by own_term
+            for (int u = 0; u < B; u++) { jj[u] = __ffs((int)m) - 1; m &= m - 1u; tq[u] = sT[tid + jj[u] * NT]; }
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int j = jj[u];
+                // class A (z'=1): sat(cK S); class B (z'=0): sat(1 - cK S); neither: 1 -- one FFMA.SAT with selected constants
+                const bool a = (Amask >> j) & 1u, b = (Bmask >> j) & 1u;
+                const float mul = a ? cK : (b ? -cK : 0.f), add = a ? 0.f : 1.f;
+                const float fd = __saturatef(fmaf(mul, tq[u].x + tq[u].y, add));
+                pd *= fd;
+#pragma unroll
+                for (int c = 0; c < SP; c++) {
+                    const float w = weight(tq[u], kk[c], kx[c], ky[c], lawk[c]);
+                    const float fn = __saturatef(fmaf(mul, fmaf(sgn[c], w, tq[u].x) + tq[u].y, add));
+                    pn[c] *= j == kj[c] ? fd : fn;        // the candidate's own cell is handled by own_term
+                }
             }
-            if (++cnt == 4 || m == 0u) {                  // products of at most 4 factors stay far from underflow
+            cnt += B;
+        };
+        while (m) {                                       // warp-uniform
+            if (SP <= 2 && (m & (m - 1u))) slots(std::integral_constant<int, 2>());
+            else slots(std::integral_constant<int, 1>());
+            if (cnt >= 4 || m == 0u) {                    // products of at most 4 factors stay far from underflow
                 const float lpd = Num<float>::lg2(pd);
 #pragma unroll
                 for (int c = 0; c < SP; c++) { acc[c] += Num<float>::lg2(pn[c]) - lpd; pn[c] = 1.f; }
