@@ -257,7 +257,10 @@ def test_fp64_sweeps_follow_the_cpu_twin(geom, detect, sample_ab):
 @pytest.mark.parametrize("geom,n,C,T,variant", [(O.GEOM_COORDS, 700, 3, 6, None), (O.GEOM_LINEAR, 2100, 2, 4, None),
                                                  (O.GEOM_DENSE, 300, 5, 5, None), (O.GEOM_COORDS, 1500, 19, 9, None),
                                                  (O.GEOM_COORDS, 900, 4, 7, "dieoff"), (O.GEOM_LINEAR, 600, 3, 6, "loss"),
-                                                 (O.GEOM_COORDS, 300, 2, 41, None)])
+                                                 (O.GEOM_COORDS, 300, 2, 41, None),
+                                                 # above 3,000 patches the spatially culled scan (k_sweep_y_cull) and the culled k_conn run
+                                                 (O.GEOM_COORDS, 6000, 2, 4, None), (O.GEOM_LINEAR, 5200, 2, 3, None),
+                                                 (O.GEOM_COORDS, 4100, 3, 5, "dieoff")])
 def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T, variant):
     """The FP32 throughput sweep (cluster-split, two-float S, product-of-factors logs) draws from the
     same thresholds as the FP64 path: after one sweep from the same state the latent states agree
