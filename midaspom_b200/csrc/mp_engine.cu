@@ -54,7 +54,11 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     // FP32 engines on landscapes with positions skip source tiles out of reach (see CONN_CULL_LOG2); FP64 never culls
     constexpr bool CAN_CULL = sizeof(R) == 4 && GEOM != MP_GEOM_DENSE;
     const bool cull = CAN_CULL && h->conn_cull && h->have_boxes;
-#define MP_CONN(NYB) do { if (cull) k_conn<R, GEOM, NYB, CAN_CULL><<<grid, CONN_TILE, 0, h->stream>>>(a); \
+    // culled CTAs do unequal work: with fewer than ~4 of them per SM, one target per thread (twice the CTAs) balances better
+    const bool narrow = cull && (long long)grid.x * grid.y * grid.z < 4LL * h->sm_count;
+    if (narrow) grid.x = (a.k_hi - a.k_lo + CONN_TILE - 1) / CONN_TILE;
+#define MP_CONN(NYB) do { if (narrow) k_conn<R, GEOM, NYB, CAN_CULL, 1><<<grid, CONN_TILE, 0, h->stream>>>(a); \
+                          else if (cull) k_conn<R, GEOM, NYB, CAN_CULL><<<grid, CONN_TILE, 0, h->stream>>>(a); \
                           else k_conn<R, GEOM, NYB, false><<<grid, CONN_TILE, 0, h->stream>>>(a); } while (0)
     if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
     else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);

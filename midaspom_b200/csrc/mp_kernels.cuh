@@ -75,14 +75,14 @@ template <typename R> struct ConnArgs {
 // engine never culls.
 constexpr float CONN_CULL_LOG2 = -28.f;
 
-template <typename R, int GEOM, int NYB, bool CULL = false>
+template <typename R, int GEOM, int NYB, bool CULL = false, int TGT = CONN_TGT>
 __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
 {
-    // Each thread owns CONN_TGT targets (k, k + 128, ...) and NYB year accumulators per target.
+    // Each thread owns TGT targets (k, k + 128, ...) and NYB year accumulators per target.
     // Per source of the tile: coordinates, area constant, and the year bits expanded to 0.0 / 1.0
     // doubles, so that the contraction over years is a chain of DFMAs
     //   acc[t] = fma(w, y01[t], acc[t])   (== acc[t] + w or acc[t], exactly)
-    // fed by broadcast LDS.128; the y01 loads are shared by the CONN_TGT targets of the thread.
+    // fed by broadcast LDS.128; the y01 loads are shared by the TGT targets of the thread.
     __shared__ R sx[CONN_TILE], sy[CONN_TILE], saw[CONN_TILE];
     __shared__ uint32_t sbits[CONN_TILE];
     __shared__ int sl[CULL ? CONN_TILE : 1];                          // culled variant: patch number of the tile's sources
@@ -91,22 +91,22 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
     // first target of the thread: patch kbase, then kbase + 128 (coalesced stores); in the culled variant scan-order
     // slots kbase, kbase + 32, so that a warp owns 64 consecutive slots -- one spatially compact group
     const int kstep = CULL ? 32 : CONN_TILE;
-    const int kbase = a.k_lo + blockIdx.x * CONN_TILE * CONN_TGT + (CULL ? (tid >> 5) * 32 * CONN_TGT + (tid & 31) : tid);
+    const int kbase = a.k_lo + blockIdx.x * CONN_TILE * TGT + (CULL ? (tid >> 5) * 32 * TGT + (tid & 31) : tid);
     const mp_params *parp = set ? a.par[1] : a.par[0];
     const R apre = alpha_pre<R>(parp[c].alpha);
     const R *aw = (set ? a.aw[1] : a.aw[0]) + (size_t)c * n;
     double *Sout = (set ? a.S[1] : a.S[0]) + (size_t)c * a.ntrans * n;
-    R tx[CONN_TGT], ty[CONN_TGT];
-    int kp[CONN_TGT];                                                 // patch number of the thread's targets (-1: none)
+    R tx[TGT], ty[TGT];
+    int kp[TGT];                                                 // patch number of the thread's targets (-1: none)
 #pragma unroll
-    for (int g = 0; g < CONN_TGT; g++) {
+    for (int g = 0; g < TGT; g++) {
         const int k = kbase + g * kstep;
         kp[g] = k < a.k_hi ? (CULL ? a.perm[k] : k) : -1;
         tx[g] = 0; ty[g] = 0;
         if (GEOM == MP_GEOM_COORDS && kp[g] >= 0) { tx[g] = a.ls.px[kp[g]]; ty[g] = a.ls.py[kp[g]]; }
     }
     // boxes {xmin, xmax, ymin, ymax} of the CTA's targets and of the warp's targets (unions of 32-slot group boxes)
-    float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f), wbox = tbox;
+    float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f), gbox[TGT];
     auto box_union = [](const float4 &p, const float4 &q) { return make_float4(fminf(p.x, q.x), fmaxf(p.y, q.y), fminf(p.z, q.z), fmaxf(p.w, q.w)); };
     // log2 of the largest distance factor exp(-alpha d) between two boxes (apre = -alpha log2 e), with a rounding margin
     auto reach_log2 = [&](const float4 &p, const float4 &q) {
@@ -114,29 +114,32 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
         return (float)apre * (0.9999f * sqrtf(dx * dx + dy * dy));
     };
     if (CULL) {
-        const int g0 = (a.k_lo + blockIdx.x * CONN_TILE * CONN_TGT) / 32, gend = (a.k_hi + 31) / 32;
+        const int g0 = (a.k_lo + blockIdx.x * CONN_TILE * TGT) / 32, gend = (a.k_hi + 31) / 32;
         tbox = a.box32[g0];
-        for (int i = 1; i < CONN_TILE * CONN_TGT / 32; i++) if (g0 + i < gend) tbox = box_union(tbox, a.box32[g0 + i]);
-        const int w0 = g0 + (tid >> 5) * CONN_TGT;
-        wbox = a.box32[min(w0, gend - 1)];
-        for (int i = 1; i < CONN_TGT; i++) if (w0 + i < gend) wbox = box_union(wbox, a.box32[w0 + i]);
+        for (int i = 1; i < CONN_TILE * TGT / 32; i++) if (g0 + i < gend) tbox = box_union(tbox, a.box32[g0 + i]);
+        const int w0 = g0 + (tid >> 5) * TGT;
+#pragma unroll
+        for (int g = 0; g < TGT; g++) gbox[g] = a.box32[min(w0 + g, gend - 1)];   // the warp's g-th group of 32 targets
     }
     for (int w = 0; w < a.nwords; w++) {
         const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
-        double acc[CONN_TGT][NYB];
+        double acc[TGT][NYB];
 #pragma unroll
-        for (int g = 0; g < CONN_TGT; g++)
+        for (int g = 0; g < TGT; g++)
 #pragma unroll
             for (int t = 0; t < NYB; t++) acc[g][t] = 0.0;
         // one source of the tile against the thread's targets
+        bool far[TGT];                                                 // culled variant: group g is out of reach of the 32 sources at hand
+#pragma unroll
+        for (int g = 0; g < TGT; g++) far[g] = false;
         auto source = [&](int l0, int j) {
             if (sbits[j] == 0) return;                                 // tile-uniform: source empty in every year
-            double wd[CONN_TGT];
+            double wd[TGT];
             const int lj = CULL ? sl[j] : l0 + j;
 #pragma unroll
-            for (int g = 0; g < CONN_TGT; g++) {
+            for (int g = 0; g < TGT; g++) {
                 R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], kp[g], lj, tx[g], ty[g], sx[j], sy[j]);
-                if (lj == kp[g]) wgt = 0;                               // l != k  (main_MIDASPOM.c:354)
+                if (lj == kp[g] || (CULL && far[g])) wgt = 0;           // l != k  (main_MIDASPOM.c:354)
                 wd[g] = (double)wgt;
             }
             const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
             for (int t2 = 0; t2 < NYB / 2; t2++) {
                 const double2 m = yb[t2];
 #pragma unroll
-                for (int g = 0; g < CONN_TGT; g++) {
+                for (int g = 0; g < TGT; g++) {
                     acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
                     acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
                 }
@@ -170,7 +173,13 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
             if (kbase < a.k_hi) {
                 if (CULL) {
                     for (int sub = 0; sub < CONN_TILE / 32; sub++) {   // warp-uniform: 32 sources against the warp's 64 targets
-                        if (l0 + 32 * sub >= n || reach_log2(wbox, a.box32[l0 / 32 + sub]) < CONN_CULL_LOG2) continue;
+                        // the decision is taken per (group of 32 targets, group of 32 sources): it does not depend on
+                        // how many groups a warp or a CTA holds, so every launch shape gives bit-identical sums
+                        if (l0 + 32 * sub >= n) continue;
+                        bool all_far = true;
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) { far[g] = reach_log2(gbox[g], a.box32[l0 / 32 + sub]) < CONN_CULL_LOG2; all_far = all_far && far[g]; }
+                        if (all_far) continue;
 #pragma unroll 2
                         for (int j = 32 * sub; j < 32 * sub + 32; j++) source(l0, j);
                     }
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
             __syncthreads();
         }
 #pragma unroll
-        for (int g = 0; g < CONN_TGT; g++) {
+        for (int g = 0; g < TGT; g++) {
             const int k = kp[g];
             if (k >= 0) {
 #pragma unroll
