@@ -52,12 +52,14 @@ def sampler_kwargs(wl):
     return dict(sample_e=1, sample_c=1, sample_alpha=1, sample_b=1, sample_p=int(wl["detect"]),
                 e_min=0.0, e_max=1.0, c_min=0.0, c_max=20.0 * c0, alpha_min=1e-4, alpha_max=1e-1, b_min=0.0, b_max=2.0,
                 p_min=0.0, p_max=1.0, n_e_steps=4, n_c_steps=1, n_adapt=200, update_z=1, update_y=1,
-                sample_K=int("era" in wl), K_min=0.1, K_max=100.0, n_v_steps=2)      # die-off variant: K on the reference's range (dieoff.c:113-114)
+                sample_K=int("era" in wl and "src_unit" not in wl), K_min=0.1, K_max=100.0, n_v_steps=2,   # die-off variant: K on the reference's range (dieoff.c:113-114)
+                sample_Ksrc=int("src_unit" in wl), sample_dsrc=int("src_unit" in wl),                       # patch-loss variant: K_L, d_L (loss.c:93-101)
+                Ksrc_min=0.1, Ksrc_max=100.0, dsrc_min=100.0, dsrc_max=4000.0)
 
 
 def start_params(wl):
     t = wl["truth"]
-    return dict(e=0.5 if "era" not in wl else t["e"], c=t["c"], alpha=t["alpha"], b=t["b"], p=t["p"], K=t.get("K", 1.0), Ksrc=0.0, dsrc=0.0)
+    return dict(e=0.5 if "era" not in wl else t["e"], c=t["c"], alpha=t["alpha"], b=t["b"], p=t["p"], K=t.get("K", 1.0), Ksrc=t.get("Ksrc", 0.0), dsrc=t.get("dsrc", 0.0))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -181,7 +183,7 @@ def run_ours(args, rank, local_rank, world):
     eng = mb.Engine(n, T, cpg, precision=mb.FP32, device=local_rank, seed=1000, detect=wl["detect"], chain_offset=first,
                     max_draws=2 * K + W + 8)
     eng.set_landscape_coords(wl["px"], wl["py"], wl["area"])
-    eng.set_source_units(None)
+    eng.set_source_units(wl.get("src_unit"))
     obs_pinned = torch.from_numpy(wl["obs"].copy()).pin_memory()
     obs_host = obs_pinned.numpy()
     eng.set_observations(obs_host)
@@ -287,7 +289,7 @@ def run_ours(args, rank, local_rank, world):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"{args.workload}: {wl['desc']}", n_patches=n, n_years=T, chains=chains_total,
                                 chains_per_gpu=cpg, geometry="planar coordinates + areas, on-the-fly weights",
-                                sampled=["e", "c", "alpha", "b"] + (["p"] if wl["detect"] else []) + (["K"] if "era" in wl else []),
+                                sampled=["e", "c", "alpha", "b"] + (["p"] if wl["detect"] else []) + (["Ksrc", "dsrc"] if "src_unit" in wl else ["K"] if "era" in wl else []),
                                 l2="flushed between timed steps (256 MiB write)", parallelism=f"chains x{world}"),
                     clocks=clk.summary(),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(obs_host.nbytes),

@@ -17,6 +17,9 @@ WORKLOADS = {
     "cfg3": dict(n=10000, T=20, chains_per_gpu=8, detect=0, desc="synthetic N=10,000 x T=20, 64 chains over 8 GPUs (8 per GPU)"),
     "cfg4": dict(n=10000, T=20, chains_per_gpu=8, detect=0, era_pre=10, K=3.0,
                  desc="synthetic N=10,000 x T=20, 8 chains per GPU, die-off variant: first 10 transitions pre-event with K_D=3 (E=e/K, C=c K S), K sampled"),
+    "cfg4l": dict(n=10000, T=20, chains_per_gpu=8, detect=0, era_pre=10, Ksrc=5.0, dsrc=500.0,
+                  desc="synthetic N=10,000 x T=20, 8 chains per GPU, patch-loss variant: first 10 transitions pre-event with an external "
+                       "source K_L=5 at unit distance d_L=500 m west of the landscape (C = c (S + K_L exp(-alpha u_k d_L))), K_L and d_L sampled"),
     "tiny": dict(n=256, T=6, chains_per_gpu=4, detect=0, desc="smoke-test size"),
     "cfg5": dict(n=100000, T=30, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=30, one chain"),
     "cfg5t": dict(n=100000, T=5, chains_per_gpu=1, detect=0, desc="synthetic N=100,000 x T=5, one chain (4 year tasks: what one of 8 GPUs scans in cfg5)"),
@@ -95,11 +98,17 @@ def make_workload(name: str, seed: int = 12345):
     c = float(TRUTH["target_mean_C"] / max(S0.mean(), 1e-30))
     y = y0
     era_pre, Kv = int(w.get("era_pre", 0)), float(w.get("K", 1.0))
+    Ksrc, dsrc = float(w.get("Ksrc", 0.0)), float(w.get("dsrc", 0.0))
+    # patch-loss variant: the habitat lost at the event was an external source before it (loss.c:86-105,365); here it lies
+    # west of the landscape, patch k at u_k distance units from it
+    src_unit = (px + 500.0) / 500.0 if Ksrc else None
     for t in range(T - 1):
         Kt = Kv if t < era_pre else 1.0                      # die-off variant: E = e/K, C = c K S before the event (dieoff.c:56-57,78)
         if t > 0 or Kt != 1.0:
             y = z[t] & (rng.random(n) > min(1.0, e / Kt))
         S = y.astype(np.float32) @ W
+        if Ksrc and t < era_pre:
+            S = S + Ksrc * np.exp(-alpha * src_unit * dsrc)
         C = np.minimum(1.0, c * Kt * S)
         z[t + 1] = np.where(y == 1, 1, rng.random(n) < C)
     obs = z.astype(np.int8)
@@ -115,4 +124,7 @@ def make_workload(name: str, seed: int = 12345):
     if era_pre:
         out["era"] = (np.arange(T - 1) < era_pre).astype(np.uint8)
         truth["K"] = Kv
+    if Ksrc:
+        out["src_unit"] = src_unit
+        truth["Ksrc"], truth["dsrc"] = Ksrc, dsrc
     return out

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python scripts/validate_recovery.py cfg3 2000 > gpurun_out/recovery_cfg3.json 2> gpurun_out/recovery_cfg3.err; tail -2 gpurun_out/recovery_cfg3.err
+timeout 600 python scripts/validate_recovery.py cfg4l 3000 > gpurun_out/recovery_cfg4l.json 2> gpurun_out/recovery_cfg4l.err; tail -2 gpurun_out/recovery_cfg4l.err
 timeout 600 python scripts/validate_recovery.py cfg4 2000 > gpurun_out/recovery_cfg4.json 2> gpurun_out/recovery_cfg4.err; tail -2 gpurun_out/recovery_cfg4.err
 timeout 600 python scripts/validate_recovery.py cfg2 4000 disperse > gpurun_out/recovery_cfg2.json 2> gpurun_out/recovery_cfg2.err; tail -2 gpurun_out/recovery_cfg2.err
 python - <<PY
