@@ -143,6 +143,8 @@ static int launch_sweep_y_fast(mp_engine *h)
                                                            h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS,
                                                            h->task_first, h->task_stride, h->d_perm);
         CK(cudaGetLastError());
+        k_order_tasks<<<1, 1024, 0, h->stream>>>(h->d_cand_count, ntask, h->task_first, h->task_stride, h->d_task_order);
+        CK(cudaGetLastError());
     }
     Timed tm(h, MP_K_SWEEP_Y);
     // threads per task, from measurements: 256 (one CTA, no DSMEM) up to 3,000 patches (cfg2: 0.27 vs 0.35 ms),
@@ -364,7 +366,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_ljac, h->d_perm, h->d_inv, h->d_tile_box };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_inv, h->d_tile_box };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -426,7 +428,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_counts, C * NCOUNT * sizeof(unsigned long long) },
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
-        { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) },
+        { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
         { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_inv, N * sizeof(int) },
         { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) },
     };

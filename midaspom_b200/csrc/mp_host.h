@@ -56,6 +56,7 @@ struct mp_engine {
     int conn_lo = 0, conn_hi = -1;        // target patches of k_conn run by this engine (patch sharding); hi < 0 = all
     void *d_tile_box = nullptr;                // float4 {xmin, xmax, ymin, ymax} per group of 32 scan-order slots (culled k_conn)
     bool have_boxes = false; int conn_cull = 1;   // MP_CONN_CULL=0 disables the culling of k_conn
+    int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
     int *d_perm = nullptr, *d_inv = nullptr;   // Morton order of the patches: perm[slot] = patch, inv[patch] = slot
     int fast_cull = 1;               // exact spatial culling in the fast sweep (MP_FAST_CULL=0 disables)
     int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides

@@ -42,7 +42,7 @@ template <int GEOM, int CS, int TPT>
 __global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_params *__restrict__ par,
                const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
-               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, int task_first, int task_stride)
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order)
 {
     static_assert(GEOM != MP_GEOM_DENSE, "culling needs positions");
     constexpr int NT = TPT / CS, NW = NT / 32, SP = TPT > 1024 ? MP_CULL_SPEC_LARGE : MP_CULL_SPEC;
@@ -54,7 +54,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
-    const int task = task_first + (blockIdx.x / CS) * task_stride;
+    const int task = order[blockIdx.x / CS];                         // longest task first (k_order_tasks)
     const int c = task / ntrans, t = task - c * ntrans;
     float4 *sT = reinterpret_cast<float4 *>(smem_raw);               // {S_hi, S_lo, x, y} (COORDS) or {S_hi, S_lo, patch, -} (LINEAR)
     float4 *ring = sT + ept * NT;                                    // 2 chunks of RC candidate records (two float4 each)
@@ -430,7 +430,7 @@ template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept)
     cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const int *)h->d_perm, (const mp_params *)h->d_par,
                           (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
-                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, h->task_first, h->task_stride));
+                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order));
     return MP_OK;
 }
 // culled variants exist for 512 threads per task (N up to 15,872) and the large-landscape geometries

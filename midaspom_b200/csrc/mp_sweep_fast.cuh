@@ -153,11 +153,28 @@ __device__ __forceinline__ float col_factor(float cK, float s, bool a, bool b)
     return f;
 }
 
+// Launch order of the scan tasks: the (chain, year) scans are sequential and of unequal length (candidates per year
+// differ), all start together and the kernel ends with the longest.  Longest first is the classic LPT rule: the CTAs
+// dispatched last -- the ones that share an SM with more neighbours, or wait for a second wave -- get the shortest scans.
+static __global__ void __launch_bounds__(1024)
+k_order_tasks(const int *__restrict__ count, int ntask, int task_first, int task_stride, int *__restrict__ order)
+{
+    for (int m = threadIdx.x; m < ntask; m += blockDim.x) {
+        const int tm = task_first + m * task_stride, cm = count[2 * tm];
+        int rank = 0;
+        for (int o = 0; o < ntask; o++) {
+            const int co = count[2 * (task_first + o * task_stride)];
+            rank += (co > cm) || (co == cm && o < m);
+        }
+        order[rank] = tm;
+    }
+}
+
 template <int GEOM, int CS, int U, int TPT>
 __global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uint8_t *__restrict__ era,
                const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
-               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, int task_first, int task_stride)
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order)
 {
     constexpr int NT = TPT / CS, NW = NT / 32;
     constexpr bool HIER = TPT / 32 > 32;                // more than 32 warps per task: reduce inside the CTA first
@@ -168,7 +185,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
-    const int task = task_first + (blockIdx.x / CS) * task_stride;      // year sharding over GPUs: every task_stride-th task
+    const int task = order[blockIdx.x / CS];        // this engine's tasks (year sharding over GPUs), longest first (k_order_tasks)
     const int c = task / ntrans, t = task - c * ntrans;
     float4 *sT = reinterpret_cast<float4 *>(smem_raw);               // {S_hi, S_lo, x, y} of own targets, slot tid + j NT
 
@@ -404,7 +421,7 @@ template <int CS, int U, int TPT> static int launch_fast(mp_engine *h, int ept)
     cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const mp_params *)h->d_par,
                           (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
-                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, h->task_first, h->task_stride));
+                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order));
     return MP_OK;
 }
 template <int CS, int TPT> static int launch_fast_u(mp_engine *h, int ept)
