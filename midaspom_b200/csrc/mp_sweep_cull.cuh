@@ -49,8 +49,9 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     constexpr bool HIER = TPT / 32 > 32;
     constexpr int NSLOT = HIER ? CS : TPT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(16) float4 red[2][2][32];
-    __shared__ __align__(16) float4 wred[HIER ? 2 : 1][2][32];
+    constexpr int NV = (SP + 3) / 4;                                 // float4 per sender in the exchange of the SP sums
+    __shared__ __align__(16) float4 red[2][2][32][NV];
+    __shared__ __align__(16) float4 wred[HIER ? 2 : 1][2][32][NV];
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
@@ -123,40 +124,57 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     const CandRec *recs = rec + (size_t)task * n;
     uint32_t uses[2] = { 0u, 0u };
 
-    // sums of SP per-thread values over the task's TPT threads (warp shuffles, then one st.async of the warp or CTA
-    // partials to every CTA of the cluster, completion counted on the destination's mbarrier)
+    // sums of SP per-thread values over the task's TPT threads (warp shuffles, then st.async of the warp or CTA
+    // partials -- NV float4 per sender -- to every CTA of the cluster, completion counted on the destination's mbarrier)
     auto all_reduce = [&](int round, float (&v)[SP]) {
         const uint32_t u = uses[round]++;
         const int p = u & 1;
-        auto pack = [&]() { return make_float4(v[0], SP > 1 ? v[1 % SP] : 0.f, SP > 2 ? v[2 % SP] : 0.f, SP > 3 ? v[3 % SP] : 0.f); };
-        auto unpack_sum = [&](const float4 &t) {
-            v[0] = warp_sum_f(t.x);
-            if (SP > 1) v[1 % SP] = warp_sum_f(t.y);
-            if (SP > 2) v[2 % SP] = warp_sum_f(t.z);
-            if (SP > 3) v[3 % SP] = warp_sum_f(t.w);
+        auto pack = [&](int q) {
+            float f[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) f[i] = 4 * q + i < SP ? v[(4 * q + i) % SP] : 0.f;
+            return make_float4(f[0], f[1], f[2], f[3]);
+        };
+        auto unpack_sum = [&](int q, const float4 &t) {
+            if (4 * q + 0 < SP) v[(4 * q + 0) % SP] = warp_sum_f(t.x);
+            if (4 * q + 1 < SP) v[(4 * q + 1) % SP] = warp_sum_f(t.y);
+            if (4 * q + 2 < SP) v[(4 * q + 2) % SP] = warp_sum_f(t.z);
+            if (4 * q + 3 < SP) v[(4 * q + 3) % SP] = warp_sum_f(t.w);
         };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < SP; c++) v[c] = warp_sum_f(v[c]);
         if (HIER) {
-            if (lane == 0) wred[round][p][wid] = pack();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) wred[round][p][wid][q] = pack(q);
+            }
             __syncthreads();
-            unpack_sum(lane < NW ? wred[round][p][lane] : zero4);
+#pragma unroll
+            for (int q = 0; q < NV; q++) unpack_sum(q, lane < NW ? wred[round][p][lane][q] : zero4);
         }
         if (CS > 1) {
             const uint32_t boff = (uint32_t)(round * 2 + p) * 8u;
             const uint32_t slot = HIER ? rank : rank * NW + wid;
-            const uint32_t roff = (uint32_t)((round * 2 + p) * 32 + (int)slot) * 16u;
-            if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 16);
-            if (lane < CS && (!HIER || wid == 0)) st_async_f32x4(red_remote + roff, pack(), bar_remote + boff);
+            const uint32_t roff = (uint32_t)(((round * 2 + p) * 32 + (int)slot) * NV) * 16u;
+            if (tid == 0) mbar_expect_tx(bar_local + boff, NSLOT * 16 * NV);
+            if (lane < CS && (!HIER || wid == 0)) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) st_async_f32x4(red_remote + roff + 16u * q, pack(q), bar_remote + boff);
+            }
             mbar_wait(bar_local + boff, (u >> 1) & 1u);
-            unpack_sum(lane < NSLOT ? red[round][p][lane] : zero4);
+#pragma unroll
+            for (int q = 0; q < NV; q++) unpack_sum(q, lane < NSLOT ? red[round][p][lane][q] : zero4);
             return;
         }
         if (HIER) return;
-        if (lane == 0) red[round][p][wid] = pack();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; q++) red[round][p][wid][q] = pack(q);
+        }
         __syncthreads();
-        unpack_sum(lane < NSLOT ? red[round][p][lane] : zero4);
+#pragma unroll
+        for (int q = 0; q < NV; q++) unpack_sum(q, lane < NSLOT ? red[round][p][lane][q] : zero4);
     };
     // weight of (candidate k, target in slot data tq)
     auto weight = [&](const float4 &tq, int k, float kx, float ky, float lawk) -> float {

@@ -154,13 +154,28 @@ class ShardedChain:
         self.eng.sweep_phase(PH_FINISH)
 
     def sweep(self, nsweeps=1):
+        """One sweep = three compute phases with a collective after the first two.  `self.phase_s` accumulates the host
+        time of each stage (every stage ends with a device synchronisation)."""
+        import time
+        acc = self.__dict__.setdefault("phase_s", dict(conn=0.0, exchange_S=0.0, scan=0.0, exchange_y=0.0, finish=0.0))
         for _ in range(nsweeps):
+            t0 = time.perf_counter()
             flags = self.phase_a()
+            t1 = time.perf_counter()
             self.exchange_a(flags)
             self.torch.cuda.synchronize()
+            t2 = time.perf_counter()
             self.phase_b()
+            self.torch.cuda.synchronize()
+            t3 = time.perf_counter()
             self.exchange_b()
+            self.torch.cuda.synchronize()
+            t4 = time.perf_counter()
             self.phase_c()
+            self.eng.synchronize()
+            t5 = time.perf_counter()
+            for k, v in zip(("conn", "exchange_S", "scan", "exchange_y", "finish"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                acc[k] += v
         self.eng.synchronize()
 
 

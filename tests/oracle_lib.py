@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         L.spom_flip_delta.restype = C.c_double
         L.spom_init_chain.argtypes = [mp, cp, C.c_uint64, C.c_uint32, C.c_int, pp, _dp, _u8p, _u8p, _dp]
         L.spom_refresh_S.argtypes = [mp, pp, _u8p, _dp]
+        L.spom_scan_order.argtypes = [mp, C.POINTER(C.c_int32)]
         L.spom_sweep.argtypes = [mp, cp, C.c_uint64, C.c_uint32, C.c_uint32, pp, _dp, _u8p, _u8p, _dp, _dp, C.c_int64, _dp]
         L.spom_sweep.restype = C.c_int64
         L.spom_sweep_chains.argtypes = [mp, cp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, pp, _dp, _u8p, _u8p,
@@ -138,6 +139,13 @@ def connectivity(m: Model, alpha, b, y_row):
     S = np.zeros(m.n)
     lib().spom_connectivity(m.ref(), alpha, b, _ptr(y_row, _u8p), _ptr(S, _dp))
     return S
+
+
+def scan_order(m: Model):
+    """Visiting order of the y scan (slot -> patch): Morton order of planar coordinates, else index order."""
+    out = np.zeros(m.n, dtype=np.int32)
+    lib().spom_scan_order(m.ref(), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out
 
 
 def transition_prob(m: Model, par: SpomParams, pre, z_old, y_mid, z_new):

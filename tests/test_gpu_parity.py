@@ -410,6 +410,19 @@ def test_fp64_variant_sampling_follows_the_cpu_twin(variant):
     assert np.unique(got[:, :, moved]).size > 3                     # the variant parameter actually moves
 
 
+def test_scan_order_equals_the_oracle_rule():
+    """mp_get_scan_order == spom_scan_order: both sides visit the patches of a year in the same order."""
+    rng = np.random.default_rng(77)
+    for geom, n in ((O.GEOM_COORDS, 1), (O.GEOM_COORDS, 37), (O.GEOM_COORDS, 5003), (O.GEOM_LINEAR, 300), (O.GEOM_DENSE, 64)):
+        spec, z, y = random_landscape(rng, n, 3, geom)
+        if geom == O.GEOM_COORDS and n > 40:
+            spec["px"][7] = spec["px"][21]; spec["py"][7] = spec["py"][21]      # a tie
+        m = O.Model(spec["obs"], geom=geom, spacing=spec.get("spacing", 100.0), px=spec.get("px"), py=spec.get("py"),
+                    dist=spec.get("dist"), area=spec.get("area"))
+        with make_engine(spec, n_chains=1, precision=mb.FP32) as eng:
+            assert (eng.scan_order() == O.scan_order(m)).all()
+
+
 def test_chain_offset_selects_the_stream():
     """A chain's random stream depends on its GLOBAL id only: chains [2,3] run alone reproduce
     chains 2,3 of a 4-chain engine (the property MIDASPOM_MPI's row split relies on, :361-372)."""

@@ -54,3 +54,33 @@ def test_sweep_keeps_state_feasible_and_S_consistent():
         # S is refreshed at the start of a sweep and then updated incrementally through the y scan
         np.testing.assert_allclose(ch.S[c], S, rtol=1e-10, atol=1e-14)
         assert np.isfinite(ch.draws[c, 5])
+
+
+def test_scan_order_is_the_morton_curve_of_planar_coordinates():
+    """The y scan visits planar landscapes along the Z-order curve (16 bits per axis over the bounding square, ties by
+    index) and linear / dense ones in index order -- the rule the CUDA engine shares (mp_get_scan_order)."""
+    rng = np.random.default_rng(5)
+    obs = np.zeros((2, 4), dtype=np.int8)
+    # unit square corners: Z order is (0,0), (1,0), (0,1), (1,1) -- x is the low bit
+    m = O.Model(obs, geom=O.GEOM_COORDS, px=np.array([1.0, 0.0, 1.0, 0.0]), py=np.array([1.0, 1.0, 0.0, 0.0]))
+    assert O.scan_order(m).tolist() == [3, 2, 1, 0]
+    n = 777
+    obs = np.zeros((2, n), dtype=np.int8)
+    px, py = rng.uniform(0, 5000, n), rng.uniform(0, 3000, n)
+    px[10] = px[500]; py[10] = py[500]                            # identical positions: index order decides
+    order = O.scan_order(O.Model(obs, geom=O.GEOM_COORDS, px=px, py=py))
+    assert sorted(order.tolist()) == list(range(n))
+    assert list(order).index(10) + 1 == list(order).index(500)
+    # independent restatement of the code: interleave the bits of the quantised coordinates
+    span = max(px.max() - px.min(), py.max() - py.min())
+    xi = np.minimum(65535.0, (px - px.min()) / span * 65535.0).astype(np.uint64)
+    yi = np.minimum(65535.0, (py - py.min()) / span * 65535.0).astype(np.uint64)
+    code = np.zeros(n, dtype=np.uint64)
+    for bit in range(16):
+        code |= ((xi >> np.uint64(bit)) & np.uint64(1)) << np.uint64(2 * bit)
+        code |= ((yi >> np.uint64(bit)) & np.uint64(1)) << np.uint64(2 * bit + 1)
+    assert (order == np.argsort(code, kind="stable")).all()
+    # consecutive visits are spatial neighbours: far closer than two random patches
+    step = np.hypot(np.diff(px[order]), np.diff(py[order]))
+    assert np.median(step) < 0.15 * np.median(np.hypot(px - px[::-1], py - py[::-1]))
+    assert O.scan_order(O.Model(obs, geom=O.GEOM_LINEAR, spacing=100.0)).tolist() == list(range(n))
