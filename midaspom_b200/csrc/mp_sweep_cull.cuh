@@ -24,7 +24,7 @@
 #include "mp_sweep_fast.cuh"
 
 // candidates evaluated per trip (1 + speculative ones), measured: cfg3 (512 threads per task) 10.0 / 10.4 / 11.1 ms for 2 / 3 / 4,
-// cfg5t (8192 threads per task, exchange-latency bound) 43.4 / 39.3 / 38.8 ms
+// cfg5t (4096 threads per task, exchange-latency bound) 43.4 / 39.3 / 38.3 ms (6: 42.9, 8: 51.3)
 #ifndef MP_CULL_SPEC
 #define MP_CULL_SPEC 2
 #endif
