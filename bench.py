@@ -422,6 +422,7 @@ def run_cfg1(args, rank):
     print(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                           ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="bundled example",
                           config=dict(cfgd, states=info["nstates"], short_states=info["nextid"], total_loglik=ltot),
+                          ms_per_step_min=float(np.min(times)) * 1e3, ms_per_step_median=float(np.median(times)) * 1e3,
                           e2e=dict(value=v, unit="likelihood evaluations/s", h2d_bytes_per_step=int(obs.nbytes), d2h_bytes_per_step=nev * 8),
                           gpu_launches=2 * args.steps)))
 

@@ -299,29 +299,40 @@ int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches
     }
     if (state_info) { state_info[0] = tb.nvar; state_info[1] = (int)tb.nstates; state_info[2] = tb.nextid; state_info[3] = maxnp; }
 
+    // one arena from the stream-ordered pool (kept by the driver between calls: no cudaMalloc / cudaFree per grid),
+    // carved into the 11 device buffers at 256-byte boundaries
     uint32_t *d_masks = nullptr, *d_short = nullptr, *d_simpp = nullptr;
     double *d_S = nullptr, *d_axis = nullptr, *d_P = nullptr, *d_lik = nullptr, *d_work = nullptr;
     int *d_np = nullptr, *d_off = nullptr;
     float *d_prior = nullptr;
+    unsigned char *arena = nullptr;
     XCK(cudaSetDevice(device));
-    XCK(cudaMalloc(&d_masks, (size_t)tb.nstates * 4));
-    XCK(cudaMalloc(&d_short, (size_t)tb.nextid * 4));
-    XCK(cudaMalloc(&d_simpp, simpp_flat.size() * 4));
-    XCK(cudaMalloc(&d_S, (size_t)tb.nstates * n * 8));
-    XCK(cudaMalloc(&d_axis, (size_t)nstep * 8));
-    XCK(cudaMalloc(&d_P, (size_t)ng * tb.nextid * tb.nextid * 8));
-    XCK(cudaMalloc(&d_lik, (size_t)ng * 8));
-    XCK(cudaMalloc(&d_work, (size_t)ng * 2 * tb.npstates[0] * maxnp * 8));
-    XCK(cudaMalloc(&d_np, (size_t)T * 4));
-    XCK(cudaMalloc(&d_off, (size_t)(T + 1) * 4));
-    XCK(cudaMalloc(&d_prior, tb.priorst.size() * 4));
-    XCK(cudaMemcpy(d_masks, tb.zmask_all.data(), (size_t)tb.nstates * 4, cudaMemcpyHostToDevice));
-    XCK(cudaMemcpy(d_short, short_masks.data(), (size_t)tb.nextid * 4, cudaMemcpyHostToDevice));
-    XCK(cudaMemcpy(d_simpp, simpp_flat.data(), simpp_flat.size() * 4, cudaMemcpyHostToDevice));
-    XCK(cudaMemcpy(d_axis, axis.data(), (size_t)nstep * 8, cudaMemcpyHostToDevice));
-    XCK(cudaMemcpy(d_np, tb.npstates.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
-    XCK(cudaMemcpy(d_off, simpp_off.data(), (size_t)(T + 1) * 4, cudaMemcpyHostToDevice));
-    XCK(cudaMemcpy(d_prior, tb.priorst.data(), tb.priorst.size() * 4, cudaMemcpyHostToDevice));
+    {
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        const size_t o_masks = carve((size_t)tb.nstates * 4), o_short = carve((size_t)tb.nextid * 4), o_simpp = carve(simpp_flat.size() * 4),
+                     o_S = carve((size_t)tb.nstates * n * 8), o_axis = carve((size_t)nstep * 8),
+                     o_P = carve((size_t)ng * tb.nextid * tb.nextid * 8), o_lik = carve((size_t)ng * 8),
+                     o_work = carve((size_t)ng * 2 * tb.npstates[0] * maxnp * 8), o_np = carve((size_t)T * 4),
+                     o_off = carve((size_t)(T + 1) * 4), o_prior = carve(tb.priorst.size() * 4);
+        static bool pool_ready = false;
+        if (!pool_ready) {                                // keep freed memory in the pool instead of returning it to the OS
+            cudaMemPool_t pool; unsigned long long keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pool_ready = true;
+        }
+        XCK(cudaMallocAsync((void **)&arena, off, 0));
+        d_masks = (uint32_t *)(arena + o_masks); d_short = (uint32_t *)(arena + o_short); d_simpp = (uint32_t *)(arena + o_simpp);
+        d_S = (double *)(arena + o_S); d_axis = (double *)(arena + o_axis); d_P = (double *)(arena + o_P); d_lik = (double *)(arena + o_lik);
+        d_work = (double *)(arena + o_work); d_np = (int *)(arena + o_np); d_off = (int *)(arena + o_off); d_prior = (float *)(arena + o_prior);
+    }
+    XCK(cudaMemcpyAsync(d_masks, tb.zmask_all.data(), (size_t)tb.nstates * 4, cudaMemcpyHostToDevice, 0));
+    XCK(cudaMemcpyAsync(d_short, short_masks.data(), (size_t)tb.nextid * 4, cudaMemcpyHostToDevice, 0));
+    XCK(cudaMemcpyAsync(d_simpp, simpp_flat.data(), simpp_flat.size() * 4, cudaMemcpyHostToDevice, 0));
+    XCK(cudaMemcpyAsync(d_axis, axis.data(), (size_t)nstep * 8, cudaMemcpyHostToDevice, 0));
+    XCK(cudaMemcpyAsync(d_np, tb.npstates.data(), (size_t)T * 4, cudaMemcpyHostToDevice, 0));
+    XCK(cudaMemcpyAsync(d_off, simpp_off.data(), (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, 0));
+    XCK(cudaMemcpyAsync(d_prior, tb.priorst.data(), tb.priorst.size() * 4, cudaMemcpyHostToDevice, 0));
     k_exact_S<<<(tb.nstates + 127) / 128, 128>>>(d_masks, tb.nstates, n, a, d, d_S);
     XCK(cudaGetLastError());
     k_exact_grid<<<ng, 256>>>(d_masks, tb.nstates, n, d_S, d_short, tb.nextid, d_axis, d_axis, nstep, T, d_np, d_off, d_simpp,
@@ -340,8 +351,7 @@ int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches
         *ltot_out = 2.0 * log(win) + log(Ltot);
     }
 done:
-    cudaFree(d_masks); cudaFree(d_short); cudaFree(d_simpp); cudaFree(d_S); cudaFree(d_axis); cudaFree(d_P);
-    cudaFree(d_lik); cudaFree(d_work); cudaFree(d_np); cudaFree(d_off); cudaFree(d_prior);
+    if (arena) cudaFreeAsync(arena, 0);
     return rc;
 }
 
