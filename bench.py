@@ -363,7 +363,6 @@ def run_sharded(args, rank, local_rank, world, wl):
                     clocks=clk.summary(), gpu_launches=int(sum(klaunch.values())),
                     collective_bytes_per_sweep=int(bytes_per_sweep), ranks_hold_identical_draws=bool(ok.item() == 1.0),
                     phase_ms_per_sweep={k: round(v / K * 1e3, 3) for k, v in sc.phase_s.items()},
-                    kernel_ms_per_sweep={k: round(v / max(K + W, 1), 3) for k, v in kms.items()},
                     e2e=dict(value=C * K / total_s, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0,
                              note="state resident; the sharded loop has no per-step host buffers"))
         print(json.dumps(line), flush=True)
