@@ -55,6 +55,7 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     constexpr bool CAN_CULL = sizeof(R) == 4 && GEOM != MP_GEOM_DENSE;
     const bool cull = CAN_CULL && h->conn_cull && h->have_boxes;
     // culled CTAs do unequal work: with fewer than ~4 of them per SM, one target per thread (twice the CTAs) balances better
+    a.mlow = h->d_mlow; a.area_max = (float)h->area_max; a.area_min = (float)h->area_min;   // bounds: launch_conn_bounds
     const bool narrow = cull && (long long)grid.x * grid.y * grid.z < 4LL * h->sm_count;
     if (narrow) grid.x = (a.k_hi - a.k_lo + CONN_TILE - 1) / CONN_TILE;
 #define MP_CONN(NYB) do { if (narrow) k_conn<R, GEOM, NYB, CAN_CULL, 1><<<grid, CONN_TILE, 0, h->stream>>>(a); \
@@ -63,6 +64,17 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
     else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);
 #undef MP_CONN
+    CK(cudaGetLastError());
+    return MP_OK;
+}
+// Culling bounds of k_conn: a lower bound of every target group's S, taken from the resident S BEFORE it is overwritten
+// or zeroed (none before the first refresh: mlow = 0, nothing is skipped).
+static int launch_conn_bounds(mp_engine *h)
+{
+    if (is64(h) || h->geom == MP_GEOM_DENSE || !h->conn_cull || !h->have_boxes) return MP_OK;
+    Timed tm(h, MP_K_SMALL);
+    k_group_min_S<<<dim3((h->cfg.n_patches + 31) / 32, h->cfg.n_chains), 32, 0, h->stream>>>(h->d_S[0], h->d_perm, h->cfg.n_patches,
+                                                                                             h->cfg.n_years - 1, h->S_valid ? 1 : 0, h->d_mlow);
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -195,6 +207,7 @@ template <typename R> static int refresh_S(mp_engine *h)
     int rc;
     if ((rc = launch_pack_y(h)) != MP_OK) return rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
+    if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
     const int rc2 = launch_conn<R>(h, 0, 1);
     if (rc2 == MP_OK) h->S_valid = true;
     return rc2;
@@ -238,6 +251,7 @@ template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out
     // The resident S is maintained by exact rank-1 updates; the FP32 engine recomputes it from scratch only
     // every MP_REFRESH_EVERY sweeps (the FP64 parity engine every sweep, like the CPU twin).
     const bool refresh = is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0 || !h->S_valid;
+    if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
     if (sharded) {   // other ranks fill the other target columns: start from zeros so that a sum over ranks assembles S
         if (refresh) CK(cudaMemsetAsync(h->d_S[0], 0, nC(h) * ycells(h) * 8, h->stream));
         if (do_ab) CK(cudaMemsetAsync(h->d_S[1], 0, nC(h) * ycells(h) * 8, h->stream));
@@ -366,7 +380,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_inv, h->d_tile_box };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_inv, h->d_tile_box, h->d_mlow };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -430,7 +444,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
         { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_inv, N * sizeof(int) },
-        { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) },
+        { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) }, { (void **)&h->d_mlow, C * ((N + 31) / 32) * sizeof(float) },
     };
     for (auto &r : reqs) {
         if ((e = cudaMalloc(r.p, r.bytes)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -459,8 +473,10 @@ static int upload_real(mp_engine *h, void *dst, const double *src, size_t n)
 static int set_area(mp_engine *h, const double *area)
 {
     h->have_area = area != nullptr;
+    h->area_max = h->area_min = 1.0;
     if (area) {
         for (size_t i = 0; i < nN(h); i++) REQUIRE(area[i] > 0.0, MP_ERR_ARG, "patch areas must be positive");
+        h->area_max = *std::max_element(area, area + nN(h)); h->area_min = *std::min_element(area, area + nN(h));
         CK(cudaMemcpy(h->d_area, area, nN(h) * 8, cudaMemcpyHostToDevice));
     }
     return MP_OK;

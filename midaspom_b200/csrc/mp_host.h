@@ -55,6 +55,8 @@ struct mp_engine {
     int task_first = 0, task_stride = 1;   // (chain, year) tasks of the y sweep run by this engine (year sharding)
     int conn_lo = 0, conn_hi = -1;        // target patches of k_conn run by this engine (patch sharding); hi < 0 = all
     void *d_tile_box = nullptr;                // float4 {xmin, xmax, ymin, ymax} per group of 32 scan-order slots (culled k_conn)
+    float *d_mlow = nullptr;                   // [chain][group] lower bound of S per group of 32 slots (k_group_min_S)
+    double area_max = 1.0, area_min = 1.0;
     bool have_boxes = false; int conn_cull = 1;   // MP_CONN_CULL=0 disables the culling of k_conn
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
     int *d_perm = nullptr, *d_inv = nullptr;   // Morton order of the patches: perm[slot] = patch, inv[patch] = slot

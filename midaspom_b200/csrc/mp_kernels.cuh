@@ -66,14 +66,33 @@ template <typename R> struct ConnArgs {
                            // patch numbers, or scan-order slots for the culled variant
     const int *perm;       // culled variant: scan-order slot -> patch (Morton order of planar landscapes)
     const float4 *box32;   // culled variant: bounding box {xmin, xmax, ymin, ymax} of every group of 32 consecutive slots
+    const float *mlow;     // culled variant: [chain][group] lower bound of the group's S over all years (0 = unknown: no culling)
+    float area_max, area_min;   // extremes of the patch areas (1, 1 without areas): A_l^b <= max(area_max^b, area_min^b)
 };
 // Culled variant (FP32 engines, landscapes with positions): targets and sources are taken in scan (Morton) order, so
-// groups of consecutive slots are spatially compact.  A tile of 128 sources is not even loaded when its box is so far
-// from the box of the CTA's 256 targets that exp(-alpha d) < 2^-28 for every pair, and each warp skips the 32-source
-// groups out of reach of its own 64 targets.  The skipped mass per target is at most 2^-28 sum_l A_l^b -- about 1e-7
-// of S on the benchmark landscapes (below FP32 resolution; the FP32 engine's tolerance is 1e-5).  The FP64 parity
-// engine never culls.
-constexpr float CONN_CULL_LOG2 = -28.f;
+// groups of 32 consecutive slots are spatially compact.  A group of 32 sources is skipped for a group of 32 targets
+// when every weight between them is below 2^-30 of the smallest S the target group currently has (k_group_min_S: the
+// resident S, any year), and a tile of 128 sources is not even loaded when that holds for all of the CTA's target
+// groups.  What is skipped is dominated by the sources just beyond the reach (2 pi R rho / alpha of them, a few
+// hundred at the benchmark density), i.e. ~1e-7 of S -- relative to each group's own S, so isolated patches with a
+// small S keep their accuracy.  Without a valid resident S (first sweep) mlow = 0 and nothing is skipped.  The FP64
+// parity engine never culls.
+constexpr float CONN_CULL_LOG2 = -30.f;
+
+// min over years and over the 32 patches of a scan-order group of the resident S (culling bound of k_conn)
+static __global__ void __launch_bounds__(32)
+k_group_min_S(const double *__restrict__ S, const int *__restrict__ perm, int n, int ntrans, int valid, float *__restrict__ mlow)
+{
+    const int g = blockIdx.x, c = blockIdx.y, slot = g * 32 + threadIdx.x, ngroups = gridDim.x;
+    float m = 3.0e38f;
+    if (valid && slot < n) {
+        const double *Sc = S + (size_t)c * ntrans * n + perm[slot];
+        for (int t = 0; t < ntrans; t++) m = fminf(m, (float)Sc[(size_t)t * n]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) mlow[(size_t)c * ngroups + g] = valid ? fmaxf(m * 0.999f, 0.f) : 0.f;
+}
 
 template <typename R, int GEOM, int NYB, bool CULL = false, int TGT = CONN_TGT>
 __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
@@ -113,13 +132,19 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
         const float dx = fmaxf(0.f, fmaxf(q.x - p.y, p.x - q.y)), dy = fmaxf(0.f, fmaxf(q.z - p.w, p.z - q.w));
         return (float)apre * (0.9999f * sqrtf(dx * dx + dy * dy));
     };
+    // skip when log2(exp(-alpha d)) < thr: thr = CONN_CULL_LOG2 + log2(mlow / max_l A_l^b) of the target group(s); -inf = never
+    float thr_cta = 0.f, thr[TGT];
     if (CULL) {
-        const int g0 = (a.k_lo + blockIdx.x * CONN_TILE * TGT) / 32, gend = (a.k_hi + 31) / 32;
-        tbox = a.box32[g0];
-        for (int i = 1; i < CONN_TILE * TGT / 32; i++) if (g0 + i < gend) tbox = box_union(tbox, a.box32[g0 + i]);
+        const int g0 = (a.k_lo + blockIdx.x * CONN_TILE * TGT) / 32, gend = (a.k_hi + 31) / 32, ngroups = (n + 31) / 32;
+        const float b = (float)parp[c].b;
+        const float law_max = fmaxf(b * log2f(a.area_max), b * log2f(a.area_min)) + 1e-3f;     // log2 of max_l A_l^b, rounded up
+        auto thr_of = [&](int g) { return CONN_CULL_LOG2 + log2f(a.mlow[(size_t)c * ngroups + g]) - law_max; };   // log2f(0) = -inf
+        tbox = a.box32[g0]; thr_cta = thr_of(g0);
+        for (int i = 1; i < CONN_TILE * TGT / 32; i++)
+            if (g0 + i < gend) { tbox = box_union(tbox, a.box32[g0 + i]); thr_cta = fminf(thr_cta, thr_of(g0 + i)); }
         const int w0 = g0 + (tid >> 5) * TGT;
 #pragma unroll
-        for (int g = 0; g < TGT; g++) gbox[g] = a.box32[min(w0 + g, gend - 1)];   // the warp's g-th group of 32 targets
+        for (int g = 0; g < TGT; g++) { gbox[g] = a.box32[min(w0 + g, gend - 1)]; thr[g] = thr_of(min(w0 + g, gend - 1)); }   // the warp's g-th group
     }
     for (int w = 0; w < a.nwords; w++) {
         const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
@@ -157,7 +182,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
             if (CULL) {                                                // CTA-uniform: is any (target, source) pair of the tile within reach?
                 float4 sb = a.box32[l0 / 32];
                 for (int i = 1; i < CONN_TILE / 32; i++) if (l0 + 32 * i < n) sb = box_union(sb, a.box32[l0 / 32 + i]);
-                if (reach_log2(tbox, sb) < CONN_CULL_LOG2) continue;
+                if (reach_log2(tbox, sb) < thr_cta) continue;
             }
             const int l = (CULL && l0 + tid < n) ? a.perm[l0 + tid] : l0 + tid;
             uint32_t bits = 0;
@@ -178,7 +203,7 @@ __global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
                         if (l0 + 32 * sub >= n) continue;
                         bool all_far = true;
 #pragma unroll
-                        for (int g = 0; g < TGT; g++) { far[g] = reach_log2(gbox[g], a.box32[l0 / 32 + sub]) < CONN_CULL_LOG2; all_far = all_far && far[g]; }
+                        for (int g = 0; g < TGT; g++) { far[g] = reach_log2(gbox[g], a.box32[l0 / 32 + sub]) < thr[g]; all_far = all_far && far[g]; }
                         if (all_far) continue;
 #pragma unroll 2
                         for (int j = 32 * sub; j < 32 * sub + 32; j++) source(l0, j);

@@ -295,6 +295,54 @@ def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T, variant):
     rel_close(S32[same], S64[same], 1e-5, floor=1e-9)
 
 
+@pytest.mark.parametrize("layout,alpha", [("clusters", 1 / 400), ("blob", 1 / 400), ("uniform", 1 / 20000), ("uniform", 1 / 100),
+                                          ("duplicates", 1 / 400), ("line", 1 / 400)])
+def test_culled_scan_on_adversarial_landscapes(layout, alpha):
+    """The spatial culling (group bounds, reach tests) must stay exact whatever the geometry: tight clusters far
+    apart, everything within one dispersal length, no culling at all (tiny alpha), almost everything culled (large
+    alpha), many patches on the same spot, patches on a line.  FP32 culled scan vs FP64 generic scan from the same
+    state: same decisions up to FP32 ties, incremental S == recomputed S."""
+    rng = np.random.default_rng(sum(map(ord, layout)) * 1000 + round(1 / alpha) % 997)
+    n, T, C = 4500, 4, 2
+    spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.5, miss=0.03)
+    if layout == "clusters":
+        cen = rng.uniform(0, 30000, (20, 2)); which = rng.integers(0, 20, n)
+        spec["px"] = cen[which, 0] + rng.normal(0, 300, n); spec["py"] = cen[which, 1] + rng.normal(0, 300, n)
+    elif layout == "blob":
+        spec["px"] = rng.uniform(0, 500, n); spec["py"] = rng.uniform(0, 500, n)
+    elif layout == "duplicates":
+        spots = rng.uniform(0, 20000, (300, 2)); which = rng.integers(0, 300, n)
+        spec["px"] = spots[which, 0].copy(); spec["py"] = spots[which, 1].copy()
+    elif layout == "line":
+        spec["px"] = rng.uniform(0, 400000, n); spec["py"] = np.full(n, 123.0)
+    m = O.Model(spec["obs"], geom=O.GEOM_COORDS, px=spec["px"], py=spec["py"], area=spec.get("area"))
+    S0 = O.connectivity(m, alpha, 0.5, y[0])
+    c = 0.3 / max(np.median(S0[S0 > 0]) if (S0 > 0).any() else 1.0, 1e-300)          # colonisation probabilities around 0.3
+    par = pdict(e=0.35, c=float(c), alpha=alpha, b=0.5)
+    sc = mb.engine.sampler_config(sample_e=0, sample_c=0, update_z=0, n_adapt=0)
+    out = {}
+    for prec in (mb.FP64, mb.FP32):
+        with make_engine(spec, n_chains=C, precision=prec, seed=23, max_draws=1) as eng:
+            eng.set_params([par] * C)
+            eng.set_state(np.stack([z] * C), np.stack([y] * C))
+            eng.set_sampler(sc)
+            eng.connectivity(fetch=False)
+            eng.sweep(1)
+            _, yy = eng.get_state()
+            out[prec] = (yy, eng.get_connectivity(), eng.connectivity())
+    y64, S64, _ = out[mb.FP64]
+    y32, S32, S32new = out[mb.FP32]
+    cand = ((z[:-1] & z[1:]) == 1).sum() * C
+    assert (y64 != y32).sum() <= max(2, 2e-3 * cand)
+    scale = max(float(np.median(S64[S64 > 0])), 1e-300)
+    rel_close(S32, S32new, 1e-6, floor=1e-6 * scale)
+    same = (y64 == y32).all(axis=2)
+    # FP32 positions: a coordinate is stored to 2^-24 of the landscape's extent, so a weight exp(-alpha d) carries a
+    # relative error of up to ~4 alpha extent 2^-24 on top of the FP32 arithmetic (1e-5) -- DESIGN.md section 5
+    extent = max(np.ptp(spec["px"]), np.ptp(spec["py"]), 1.0)
+    rel_close(S32[same], S64[same], 1e-5 + 4 * alpha * extent * 2.0 ** -24, floor=1e-6 * scale)
+
+
 def test_fast_sweep_variants_agree(monkeypatch):
     """The launch geometry of the fast sweep (threads per task, cluster size, in-CTA pre-reduction for
     the large-N variants) must not change what a chain does: the Philox thresholds are keyed by cell,
@@ -344,14 +392,15 @@ def test_large_landscape_sweep_is_consistent():
     assert np.isfinite(d[:, :, 5]).all() and (yy != y[None]).sum() > 1000
 
 
-def test_sharded_chain_equals_single_engine():
+@pytest.mark.parametrize("n", [3000, 5200])          # 5200: the culled scan and the culled k_conn run sharded
+def test_sharded_chain_equals_single_engine(n):
     """BASELINE config 5 path: one chain sharded over W ranks (connectivity by target patches, y scan by
     years, replicated decisions) must reproduce the single-engine run bit for bit.  The W ranks are
     emulated in one process on one GPU, with the NCCL all-reduce replaced by an explicit sum."""
     import torch
     from midaspom_b200 import distributed as D
     rng = np.random.default_rng(31)
-    n, T, C, W = 3000, 7, 2, 3
+    T, C, W = 7, 2, 3
     spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.5, miss=0.05)
     par = pdict(e=0.4, c=0.01, alpha=1 / 400, b=0.5)
     kw = dict(sample_alpha=1, sample_b=1, c_max=0.2, alpha_min=1e-4, alpha_max=1e-1, n_adapt=4)
@@ -556,8 +605,9 @@ def test_full_size_properties_cfg3():
         zg, yg = eng.get_state()
         S_inc = eng.get_connectivity()
         S_new = eng.connectivity()
-        # the FP32 engine's from-scratch S skips source groups with exp(-alpha d) < 2^-28 (k_conn, culled variant) while
-        # the rank-1 updates reach to 2^-36 of S: the two agree to ~1e-7, any lost update would show at >= 1e-4
+        # the FP32 engine's from-scratch S skips source groups whose weights are below 2^-30 of the target group's S
+        # (k_conn, culled variant) while the rank-1 updates reach to 2^-36 of S: the two agree to ~1e-7, any lost update
+        # would show at >= 1e-4
         rel_close(S_inc, S_new, 1e-6, floor=1e-9)
         obs = spec["obs"]
         for c in range(C):
