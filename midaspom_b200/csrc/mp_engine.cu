@@ -483,8 +483,8 @@ static int set_area(mp_engine *h, const double *area)
 }
 // Morton (Z-order) permutation of the patches: perm[slot] = patch, inv[patch] = slot.  Spatially adjacent
 // patches get adjacent slots, which is what makes the warp-level culling of k_sweep_y_cull effective.
-static int set_patch_order(mp_engine *h, const double *x, const double *y, double spacing = 0.0)
-{
+static int set_patch_order(mp_engine *h, const double *x, const double *y, double spacing = 0.0, double cx = 0.0, double cy = 0.0)
+{   // (cx, cy): origin of the coordinates as stored on the device (FP32 engines centre them)
     const size_t N = nN(h);
     std::vector<int> perm(N), inv(N);
     for (size_t i = 0; i < N; i++) perm[i] = (int)i;
@@ -512,7 +512,7 @@ static int set_patch_order(mp_engine *h, const double *x, const double *y, doubl
         float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
         for (size_t sI = tI * 32; sI < std::min(N, (tI + 1) * 32); sI++) {
             const int q = perm[sI];
-            const float fx = x ? (float)x[q] : (float)q * (float)spacing, fy = y ? (float)y[q] : 0.f;
+            const float fx = x ? (float)(x[q] - cx) : (float)q * (float)spacing, fy = y ? (float)(y[q] - cy) : 0.f;
             bx0 = std::min(bx0, fx); bx1 = std::max(bx1, fx); by0 = std::min(by0, fy); by1 = std::max(by1, fy);
         }
         box[tI] = make_float4(bx0, bx1, by0, by1);
@@ -550,9 +550,21 @@ int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, cons
     REQUIRE(x && y, MP_ERR_ARG, "null coordinates");
     h->geom = MP_GEOM_COORDS;
     int rc;
-    if ((rc = upload_real(h, h->d_px, x, nN(h))) != MP_OK) return rc;
-    if ((rc = upload_real(h, h->d_py, y, nN(h))) != MP_OK) return rc;
-    if ((rc = set_patch_order(h, x, y)) != MP_OK) return rc;
+    // FP32 engines store positions relative to the centre of the bounding box: only differences enter the model, and
+    // halving the largest magnitude halves the quantisation of a coordinate (2^-24 of it).  FP64 keeps the caller's values.
+    double cx = 0.0, cy = 0.0;
+    std::vector<double> xs, ys;
+    const double *ux = x, *uy = y;
+    if (!is64(h)) {
+        const auto mmx = std::minmax_element(x, x + nN(h)), mmy = std::minmax_element(y, y + nN(h));
+        cx = 0.5 * (*mmx.first + *mmx.second); cy = 0.5 * (*mmy.first + *mmy.second);
+        xs.resize(nN(h)); ys.resize(nN(h));
+        for (size_t i = 0; i < nN(h); i++) { xs[i] = x[i] - cx; ys[i] = y[i] - cy; }
+        ux = xs.data(); uy = ys.data();
+    }
+    if ((rc = upload_real(h, h->d_px, ux, nN(h))) != MP_OK) return rc;
+    if ((rc = upload_real(h, h->d_py, uy, nN(h))) != MP_OK) return rc;
+    if ((rc = set_patch_order(h, x, y, 0.0, cx, cy)) != MP_OK) return rc;      // the order comes from the caller's values, like the oracle's
     rc = set_area(h, area);
     if (rc == MP_OK) { h->have_landscape = true; h->S_valid = false; }
     return rc;
