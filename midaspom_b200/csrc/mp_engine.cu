@@ -380,7 +380,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_inv, h->d_tile_box, h->d_mlow };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_tile_box, h->d_mlow };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -443,7 +443,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
-        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_inv, N * sizeof(int) },
+        { (void **)&h->d_perm, N * sizeof(int) },
         { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) }, { (void **)&h->d_mlow, C * ((N + 31) / 32) * sizeof(float) },
     };
     for (auto &r : reqs) {
@@ -481,12 +481,12 @@ static int set_area(mp_engine *h, const double *area)
     }
     return MP_OK;
 }
-// Morton (Z-order) permutation of the patches: perm[slot] = patch, inv[patch] = slot.  Spatially adjacent
+// Morton (Z-order) permutation of the patches: perm[slot] = patch.  Spatially adjacent
 // patches get adjacent slots, which is what makes the warp-level culling of k_sweep_y_cull effective.
 static int set_patch_order(mp_engine *h, const double *x, const double *y, double spacing = 0.0, double cx = 0.0, double cy = 0.0)
 {   // (cx, cy): origin of the coordinates as stored on the device (FP32 engines centre them)
     const size_t N = nN(h);
-    std::vector<int> perm(N), inv(N);
+    std::vector<int> perm(N);
     for (size_t i = 0; i < N; i++) perm[i] = (int)i;
     if (x && y) {
         double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
@@ -501,9 +501,7 @@ static int set_patch_order(mp_engine *h, const double *x, const double *y, doubl
         }
         std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return code[a] < code[b]; });
     }
-    for (size_t s = 0; s < N; s++) inv[perm[s]] = (int)s;
     CK(cudaMemcpy(h->d_perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_inv, inv.data(), N * sizeof(int), cudaMemcpyHostToDevice));
     // bounding boxes of the groups of 32 consecutive slots (culled k_conn), in the FP32 coordinates the kernels use
     const size_t ntile = (N + 31) / 32;
     std::vector<float4> box(ntile);

@@ -59,7 +59,7 @@ struct mp_engine {
     double area_max = 1.0, area_min = 1.0;
     bool have_boxes = false; int conn_cull = 1;   // MP_CONN_CULL=0 disables the culling of k_conn
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
-    int *d_perm = nullptr, *d_inv = nullptr;   // Morton order of the patches: perm[slot] = patch, inv[patch] = slot
+    int *d_perm = nullptr;                     // scan (Morton) order of the patches: perm[slot] = patch
     int fast_cull = 1;               // exact spatial culling in the fast sweep (MP_FAST_CULL=0 disables)
     int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides
     int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
