@@ -17,9 +17,10 @@
 //  * lane j of every warp keeps the bounds of the warp's group j in registers; a removal recomputes the exact
 //    min S of every group it commits to with one REDUX (S_hi >= 0, so the IEEE bit pattern orders like the value);
 //  * the evaluated slots are taken from the ballot mask in batches of up to 4 independent dependency chains;
-//  * every trip evaluates two candidates (i and, speculatively, i+1) and reduces both sums in ONE exchange:
-//    a rejected flip (2 of 3) costs no reduction latency of its own.  The decisions are exactly those of the
-//    one-at-a-time scan: B's sum is used only if A left the state unchanged.
+//  * every trip evaluates SP consecutive candidates (the first and SP-1 speculative ones) in one pass over the union
+//    of their active groups and reduces the SP sums in ONE exchange: a rejected flip (2 of 3) costs no reduction
+//    latency of its own.  The decisions are exactly those of the one-at-a-time scan: a later candidate's sum is
+//    used only if every earlier one of the window left the state unchanged.
 #pragma once
 #include "mp_sweep_fast.cuh"
 
@@ -35,7 +36,7 @@
 namespace mp {
 
 #ifdef MP_DEBUG_CULL
-__device__ unsigned long long g_cull_dbg[4];   // [0] warp-flips, [1] evaluated slots, [2] total slots, [3] committed slots
+__device__ unsigned long long g_cull_dbg[4];   // [0] warp-trips, [1] evaluated slots, [2] total slots, [3] committed slots
 #endif
 
 template <int GEOM, int CS, int TPT>
