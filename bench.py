@@ -251,6 +251,20 @@ def run_ours(args, rank, local_rank, world):
         eng.sweep(n_ess)
         barrier()
         ess_run = time.perf_counter() - t0
+    # likelihood evaluations/s (second part of BASELINE's metric): 1 evaluation = full connectivity S of the resident
+    # state + the summed log-terms of one chain, through the public calls mp_connectivity + mp_loglik
+    barrier()
+    n_ll = 20
+    t0 = time.perf_counter()
+    for _ in range(n_ll):
+        eng.connectivity(fetch=False)
+        ll_last, _parts = eng.loglik()
+    barrier()
+    t_ll = time.perf_counter() - t0
+    tl = torch.tensor([t_ll], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    lik_evals = chains_total * n_ll / float(tl[0])
     # posterior diagnostics on everything recorded so far (gathered over ranks with NCCL)
     nd = eng.num_draws()
     d_local = torch.from_numpy(eng.get_draws(0, nd)).to(f"cuda:{local_rank}")
@@ -312,7 +326,7 @@ def run_ours(args, rank, local_rank, world):
                     gpu_launches=int(sum(klaunch.values())),
                     kernel_ms={k: round(v, 4) for k, v in kms.items()}, kernel_launches=klaunch,
                     wall_s_timed_region=t_wall,
-                    likelihood_evals_per_sec=chains_total * 2 * K / (total_ms * 1e-3),
+                    likelihood_evals_per_sec=lik_evals,
                     ess_per_sec=ess_min / run_s if run_s > 0 else None,
                     ess=dict(min_ess=ess_min, seconds=run_s, sweeps=(n_ess // 2 if ess_run is not None else nd - W),
                              note="min over sampled parameters of the summed per-chain ESS (Geyer), second half of a separate "
