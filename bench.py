@@ -145,7 +145,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     if args.workload.startswith("cfg5"):
-        print(json.dumps(dict(impl="reference", unavailable="N=100,000: one connectivity evaluation is 1e10 pair terms (minutes per "
+        emit(json.dumps(dict(impl="reference", unavailable="N=100,000: one connectivity evaluation is 1e10 pair terms (minutes per "
                               "sweep on the host); no CPU arm for this workload")), flush=True)
         return
     from midaspom_b200 import synth
@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
                             geometry="planar coordinates + areas"),
                 cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                 e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -338,7 +338,7 @@ def run_ours(args, rank, local_rank, world):
                 line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
             except Exception as ex:  # the oracle is test infrastructure: never let it break the GPU line
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="port", sample=f"failed: {ex}")
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.barrier()
@@ -397,7 +397,7 @@ def run_sharded(args, rank, local_rank, world, wl):
                     phase_ms_per_sweep={k: round(v / K * 1e3, 3) for k, v in sc.phase_s.items()},
                     e2e=dict(value=C * K / total_s, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0,
                              note="state resident; the sharded loop has no per-step host buffers"))
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line), flush=True)
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -417,7 +417,7 @@ def run_cfg1(args, rank):
     if args.impl == "reference":
         exe = ROOT / "oracle" / "_ref" / "MIDASPOM.out"
         if not exe.exists():
-            print(json.dumps(dict(impl="reference", unavailable="oracle/_ref/MIDASPOM.out not built (no /root/reference at build time)")))
+            emit(json.dumps(dict(impl="reference", unavailable="oracle/_ref/MIDASPOM.out not built (no /root/reference at build time)")))
             return
         tmp = tempfile.mkdtemp()
         times = []
@@ -428,7 +428,7 @@ def run_cfg1(args, rank):
                 times.append(time.perf_counter() - t0)
         t = float(np.mean(times))
         v = nev / t
-        print(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=args.gpus, steps=args.steps,
+        emit(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=args.gpus, steps=args.steps,
                               warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                               data="bundled example", impl="reference", config=cfgd,
                               cpu_baseline=dict(value=v, unit="likelihood evaluations/s", cores=1, kind="reference",
@@ -450,7 +450,7 @@ def run_cfg1(args, rank):
             times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
     v = nev / t
-    print(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+    emit(json.dumps(dict(metric="likelihood_evals_per_sec", value=v, unit="likelihood evaluations/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                           ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="bundled example",
                           config=dict(cfgd, states=info["nstates"], short_states=info["nextid"], total_loglik=ltot),
                           ms_per_step_min=float(np.min(times)) * 1e3, ms_per_step_median=float(np.median(times)) * 1e3,
@@ -458,7 +458,23 @@ def run_cfg1(args, rank):
                           gpu_launches=2 * args.steps)))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line, flush=True):
+    """The ONE JSON line of the contract goes to the process's real stdout; everything else any library writes to
+    file descriptor 1 (NCCL prints its version there under torchrun) has been redirected to stderr by main()."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + "\n")
+    if flush:
+        out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
