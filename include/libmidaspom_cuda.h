@@ -129,8 +129,10 @@ int mp_sweep(mp_engine *h, int nsweeps);            /* asynchronous on the engin
 int mp_synchronize(mp_engine *h);
 /* One chain sharded over several GPUs (large N): every rank holds a full replica and runs the four phases of
  * a sweep with a collective in between (midaspom_b200/distributed.py: ShardedChain).
- *   mp_set_shard: this engine evaluates the connectivity of target patches [conn_lo, conn_hi) only (conn_hi < 0:
- *     all) and scans the (chain, year) tasks task_first, task_first + task_stride, ... only.
+ *   mp_set_shard: this engine evaluates the connectivity of the targets [conn_lo, conn_hi) only (conn_hi < 0: all;
+ *     positions in the Morton order of the patches on landscapes with positions, patch numbers otherwise; multiples
+ *     of 256 except for the last rank) and scans the (chain, year) tasks task_first, task_first + task_stride, ... only.
+ *     The other targets' columns of S / S_prop are left zero so that a sum over ranks assembles them.
  *   mp_sweep_phase: 0 proposal + connectivity (sum S / S_prop over ranks afterwards; flags_out bit 0: resident S
  *     recomputed, bit 1: proposal computed), 1 Metropolis decisions + z update, 2 y scan of the owned tasks
  *     (exchange the owned rows of y and S afterwards), 3 e/p update + record.  mp_sweep == the four phases. */
