@@ -177,6 +177,22 @@ int mp_get_stream(mp_engine *h, void **stream);
 int mp_set_timing(mp_engine *h, int enabled);
 /* accumulated since the last call with reset != 0: ms[MP_K_NCAT], launches[MP_K_NCAT] */
 int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset);
+/* Work actually executed by the hot kernels since the last reset (always on: warp-local counts, one atomic per warp and
+ * launch).  Used by bench.py so that roofline fractions count executed work, not the dense algorithm's:
+ *   MP_CNT_SCAN_TRIPS    warp-trips of the culled y scan (one trip = one exchange of SP candidate sums)
+ *   MP_CNT_SCAN_EXEC     (candidate, group of 32 targets) evaluations executed, speculative ones included
+ *   MP_CNT_SCAN_RETIRED  the part of MP_CNT_SCAN_EXEC that belongs to candidates decided in their trip
+ *   MP_CNT_SCAN_COMMIT   (accepted flip, group of 32 targets) rank-1 updates of S
+ *   MP_CNT_SCAN_DENSE    (candidate, target) pairs of the unculled scans (k_sweep_y_fast, k_sweep_y)
+ *   MP_CNT_CONN_EXEC     (group of 32 targets, group of 32 sources) tiles of k_conn evaluated
+ *   MP_CNT_CONN_TOTAL    the same, culled ones included
+ *   MP_CNT_GEMM_TILES    128 x 128 x 64 tensor-core tiles issued by the fixed-(alpha, b) connectivity path */
+enum { MP_CNT_SCAN_TRIPS = 0, MP_CNT_SCAN_EXEC = 1, MP_CNT_SCAN_RETIRED = 2, MP_CNT_SCAN_COMMIT = 3, MP_CNT_SCAN_DENSE = 4,
+       MP_CNT_CONN_EXEC = 5, MP_CNT_CONN_TOTAL = 6, MP_CNT_GEMM_TILES = 7, MP_CNT_N = 8 };
+int mp_get_work_counters(mp_engine *h, uint64_t *out /* MP_CNT_N */, int reset);
+/* launch geometry of the last y scan: out4 = threads per (chain, year) task, CTAs per cluster, candidates evaluated per
+ * trip (1 + speculative), 1 if the spatially culled kernel ran (0: k_sweep_y_fast; all 0: the generic FP64 k_sweep_y) */
+int mp_get_scan_geometry(mp_engine *h, int *out4);
 /* micro-benchmarks on the engine's device: out[0] MUFU.EX2 Gop/s, out[1] FP32 FMA GFMA/s,
  * out[2] FP64 add Gop/s, out[3] device copy GB/s (read+write) */
 int mp_probe_peaks(mp_engine *h, double *out4);

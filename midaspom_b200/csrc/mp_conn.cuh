@@ -1,0 +1,286 @@
+// mp_conn.cuh -- the fused on-the-fly dispersal-kernel x occupancy contraction (main_MIDASPOM.c:350-358):
+//     S[chain][t][k] = sum_{l != k} A_l^b exp(-alpha d_kl) y[chain][t][l]           for every transition t at once.
+//
+//  k_pack_sources  one 16-byte (FP32) / 32-byte (FP64) record {x, y, area constant, year bit word} per (parameter set,
+//                  chain, 32-year word, scan-order slot): the sources of k_conn as one contiguous stream
+//  k_group_min_S   lower bound of S per group of 32 scan-order slots (culling bound)
+//  k_conn          one thread owns TGT target patches and NYB year accumulators per target.  Source records arrive
+//                  NTHR at a time through a two-stage shared-memory ring filled by the TMA engine (cp.async.bulk,
+//                  completion counted on an mbarrier), so the loads of tile i+1 overlap the arithmetic of tile i; the
+//                  dispersal weight is evaluated once per (target, source) pair and contracted over the years with
+//                  acc[t] = fma(w, y01[t], acc[t]) (exactly acc[t] + w or acc[t]).  FP64 accumulation in both precisions so
+//                  that later rank-1 removals of the same FP32 weight by the y scan cancel exactly.
+#pragma once
+#include "mp_device.cuh"
+
+namespace mp {
+
+constexpr int CONN_PAD = 128;       // the record stream of a (set, chain, word) is padded to whole tiles (zero records)
+
+template <typename R> struct SrcRec;
+template <> struct __align__(16) SrcRec<float> { float x, y, aw; uint32_t bits; };
+template <> struct __align__(16) SrcRec<double> { double x, y, aw; uint32_t bits, pad; };
+
+inline __host__ __device__ int conn_npad(int n) { return (n + CONN_PAD - 1) / CONN_PAD * CONN_PAD; }
+
+// grid (ceil(npad / 256), chains, nwords); writes the records of the parameter sets in set_mask (bit 0: resident, bit 1: proposal)
+template <typename R>
+__global__ void k_pack_sources(Landscape<R> ls, const int *__restrict__ perm, const R *__restrict__ aw0, const R *__restrict__ aw1,
+                               const uint8_t *__restrict__ y, int ntrans, int nwords, int set_mask, SrcRec<R> *__restrict__ rec)
+{
+    const int n = ls.n, npad = conn_npad(n), c = blockIdx.y, w = blockIdx.z, C = gridDim.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad) return;
+    SrcRec<R> r;
+    memset(&r, 0, sizeof r);
+    int q = -1;
+    if (s < n) {
+        q = perm[s];
+        if (ls.px) { r.x = ls.px[q]; r.y = ls.py[q]; }
+        const uint8_t *yc = y + (size_t)c * ntrans * n;
+        uint32_t bits = 0;
+        const int t1 = min(32, ntrans - 32 * w);
+        for (int t = 0; t < t1; t++) bits |= (uint32_t)(yc[(size_t)(32 * w + t) * n + q] != 0) << t;
+        r.bits = bits;
+    }
+#pragma unroll
+    for (int set = 0; set < 2; set++) {
+        if (!((set_mask >> set) & 1)) continue;
+        if (q >= 0) r.aw = (set ? aw1 : aw0)[(size_t)c * n + q];
+        rec[(((size_t)set * C + c) * nwords + w) * npad + s] = r;
+    }
+}
+
+template <typename R> struct ConnArgs {
+    Landscape<R> ls;
+    const mp_params *par[2];
+    double *S[2];
+    const SrcRec<R> *rec;  // [set][chain][word][npad], scan order
+    int ntrans, nwords, nchains;
+    int set_base;          // first parameter set of this launch (blockIdx.z counts from it)
+    int k_lo, k_hi;        // target slots [k_lo, k_hi) of this launch (patch sharding over GPUs; whole range otherwise)
+    const int *perm;       // scan-order slot -> patch (the identity for linear and dense landscapes)
+    const float4 *box32;   // culled variant: bounding box {xmin, xmax, ymin, ymax} of every group of 32 consecutive slots
+    const float *mlow;     // culled variant: [chain][group] lower bound of the group's S over all years (0 = unknown: no culling)
+    float area_max, area_min;   // extremes of the patch areas (1, 1 without areas): A_l^b <= max(area_max^b, area_min^b)
+    unsigned long long *stats;  // MP_CNT_CONN_* work counters
+};
+// Culled variant (FP32 engines, landscapes with positions): slots follow the scan (Morton) order, so groups of 32
+// consecutive slots are spatially compact.  A group of 32 sources is skipped for a group of 32 targets when every weight
+// between them is below 2^-30 of the smallest S the target group currently has (k_group_min_S: the resident S, any year),
+// and a tile of sources is not even loaded when that holds for all of the CTA's target groups.  What is skipped is
+// dominated by the sources just beyond the reach (2 pi R rho / alpha of them, a few hundred at the benchmark density),
+// i.e. ~1e-7 of S -- relative to each group's own S, so isolated patches with a small S keep their accuracy.  Without a
+// valid resident S (first sweep) mlow = 0 and nothing is skipped.  The decision is taken per (group of 32 targets, group
+// of 32 sources): it does not depend on the launch shape, so every launch shape gives bit-identical sums.  The FP64 parity
+// engine never culls.
+constexpr float CONN_CULL_LOG2 = -30.f;
+
+// min over years and over the 32 patches of a scan-order group of the resident S (culling bound of k_conn)
+static __global__ void __launch_bounds__(32)
+k_group_min_S(const double *__restrict__ S, const int *__restrict__ perm, int n, int ntrans, int valid, float *__restrict__ mlow)
+{
+    const int g = blockIdx.x, c = blockIdx.y, slot = g * 32 + threadIdx.x, ngroups = gridDim.x;
+    float m = 3.0e38f;
+    if (valid && slot < n) {
+        const double *Sc = S + (size_t)c * ntrans * n + perm[slot];
+        for (int t = 0; t < ntrans; t++) m = fminf(m, (float)Sc[(size_t)t * n]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) mlow[(size_t)c * ngroups + g] = valid ? fmaxf(m * 0.999f, 0.f) : 0.f;
+}
+
+// ---- TMA bulk copy (global -> shared, completion on an mbarrier) and the mbarrier primitives it needs
+__device__ __forceinline__ uint32_t conn_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void conn_mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void conn_mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void conn_mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity), "r"(20000u) : "memory");
+}
+__device__ __forceinline__ void conn_bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <typename R, int GEOM, int NYB, bool CULL, int TGT, int NTHR>
+__global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
+{
+    static_assert(CONN_PAD % NTHR == 0 && NTHR % 32 == 0, "tiles must divide the padding of the record stream");
+    __shared__ __align__(128) SrcRec<R> srec[2][NTHR];                // two-stage ring of source tiles (TMA destination)
+    __shared__ __align__(16) double sy01[NTHR][NYB];                  // year bits of the current tile as 0.0 / 1.0
+    __shared__ __align__(8) unsigned long long full[2];
+    const int n = a.ls.n, npad = conn_npad(n), c = blockIdx.y, set = blockIdx.z + a.set_base, tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int slot0 = a.k_lo + blockIdx.x * NTHR * TGT;              // first target slot of the CTA
+    const int kbase = slot0 + wid * 32 * TGT + lane;                 // the thread's targets: slots kbase, kbase + 32, ...: a warp owns TGT groups
+    const mp_params *parp = set ? a.par[1] : a.par[0];
+    const R apre = alpha_pre<R>(parp[c].alpha);
+    double *Sout = (set ? a.S[1] : a.S[0]) + (size_t)c * a.ntrans * n;
+    R tx[TGT], ty[TGT];
+    int ks[TGT], kp[TGT];                                            // slot and patch number of the thread's targets (-1: none)
+#pragma unroll
+    for (int g = 0; g < TGT; g++) {
+        const int k = kbase + g * 32;
+        ks[g] = k < a.k_hi ? k : -1;
+        kp[g] = k < a.k_hi ? a.perm[k] : -1;
+        tx[g] = 0; ty[g] = 0;
+        if (GEOM == MP_GEOM_COORDS && kp[g] >= 0) { tx[g] = a.ls.px[kp[g]]; ty[g] = a.ls.py[kp[g]]; }
+    }
+    if (tid == 0) {
+        conn_mbar_init(conn_smem_u32(&full[0]), 1); conn_mbar_init(conn_smem_u32(&full[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // boxes {xmin, xmax, ymin, ymax} of the CTA's targets and of the warp's target groups
+    float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f), gbox[TGT];
+    auto box_union = [](const float4 &p, const float4 &q) { return make_float4(fminf(p.x, q.x), fmaxf(p.y, q.y), fminf(p.z, q.z), fmaxf(p.w, q.w)); };
+    // log2 of the largest distance factor exp(-alpha d) between two boxes (apre = -alpha log2 e), with a rounding margin
+    auto reach_log2 = [&](const float4 &p, const float4 &q) {
+        const float dx = fmaxf(0.f, fmaxf(q.x - p.y, p.x - q.y)), dy = fmaxf(0.f, fmaxf(q.z - p.w, p.z - q.w));
+        return (float)apre * (0.9999f * sqrtf(dx * dx + dy * dy));
+    };
+    // skip when log2(exp(-alpha d)) < thr: thr = CONN_CULL_LOG2 + log2(mlow / max_l A_l^b) of the target group(s); -inf = never
+    float thr_cta = 0.f, thr[TGT];
+    const int gend = (a.k_hi + 31) / 32;
+    if (CULL) {
+        const int g0 = slot0 / 32, ngroups = (n + 31) / 32;
+        const float b = (float)parp[c].b;
+        const float law_max = fmaxf(b * log2f(a.area_max), b * log2f(a.area_min)) + 1e-3f;     // log2 of max_l A_l^b, rounded up
+        auto thr_of = [&](int g) { return CONN_CULL_LOG2 + log2f(a.mlow[(size_t)c * ngroups + g]) - law_max; };   // log2f(0) = -inf
+        tbox = a.box32[g0]; thr_cta = thr_of(g0);
+        for (int i = 1; i < NTHR * TGT / 32; i++)
+            if (g0 + i < gend) { tbox = box_union(tbox, a.box32[g0 + i]); thr_cta = fminf(thr_cta, thr_of(g0 + i)); }
+        const int w0 = g0 + wid * TGT;
+#pragma unroll
+        for (int g = 0; g < TGT; g++) { gbox[g] = a.box32[min(w0 + g, gend - 1)]; thr[g] = thr_of(min(w0 + g, gend - 1)); }   // the warp's g-th group
+    }
+    const int ntile = (n + NTHR - 1) / NTHR;
+    // first tile >= i with a (target, source) pair within reach of the CTA (CTA-uniform)
+    auto next_tile = [&](int i) {
+        if (!CULL) return i;
+        for (; i < ntile; i++) {
+            float4 sb = a.box32[i * (NTHR / 32)];
+            for (int u = 1; u < NTHR / 32; u++) if (i * NTHR + 32 * u < n) sb = box_union(sb, a.box32[i * (NTHR / 32) + u]);
+            if (!(reach_log2(tbox, sb) < thr_cta)) break;
+        }
+        return i;
+    };
+    const bool warp_live = slot0 + wid * 32 * TGT < a.k_hi;          // the warp has at least one target
+    bool gvalid[TGT];                                                // the warp's g-th target group lies inside the launch's range
+#pragma unroll
+    for (int g = 0; g < TGT; g++) gvalid[g] = slot0 + (wid * TGT + g) * 32 < a.k_hi;
+    uint32_t nexec = 0;                                              // (target group, source group) tiles evaluated by this warp
+    uint32_t phase = 0u;                                             // bit s: parity the next wait on stage s expects
+    int stage = 0;
+    for (int w = 0; w < a.nwords; w++) {
+        const SrcRec<R> *rw = a.rec + (((size_t)set * a.nchains + c) * a.nwords + w) * npad;
+        auto issue = [&](int tile, int st) {                         // thread 0: one bulk copy of a whole tile of records
+            const uint32_t bar = conn_smem_u32(&full[st]);
+            conn_mbar_expect_tx(bar, (uint32_t)(NTHR * sizeof(SrcRec<R>)));
+            conn_bulk_load(conn_smem_u32(&srec[st][0]), rw + (size_t)tile * NTHR, (uint32_t)(NTHR * sizeof(SrcRec<R>)), bar);
+        };
+        double acc[TGT][NYB];
+#pragma unroll
+        for (int g = 0; g < TGT; g++)
+#pragma unroll
+            for (int t = 0; t < NYB; t++) acc[g][t] = 0.0;
+        bool far[TGT];                                               // culled variant: group g is out of reach of the 32 sources at hand
+#pragma unroll
+        for (int g = 0; g < TGT; g++) far[g] = false;
+        int cur = next_tile(0);
+        if (tid == 0 && cur < ntile) issue(cur, stage);
+        while (cur < ntile) {
+            const int nxt = next_tile(cur + 1);
+            if (tid == 0 && nxt < ntile) issue(nxt, stage ^ 1);      // the other stage was released by the barrier that ended the previous tile
+            conn_mbar_wait(conn_smem_u32(&full[stage]), (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+            const SrcRec<R> *sr = srec[stage];
+            {
+                const uint32_t bits = sr[tid].bits;
+#pragma unroll
+                for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            const int l0 = cur * NTHR;
+            // one source of the tile against the thread's targets
+            auto source = [&](int j) {
+                const SrcRec<R> s = sr[j];                           // broadcast LDS.128
+                if (s.bits == 0) return;                             // tile-uniform: source empty in every year of this word
+                double wd[TGT];
+                const int lj = l0 + j;                               // slot of the source (== patch number without coordinates)
+#pragma unroll
+                for (int g = 0; g < TGT; g++) {
+                    if (ks[g] < 0) { wd[g] = 0.0; continue; }        // no target: nothing to address (dense: dist[source * n + target])
+                    R wgt = pair_weight<R, GEOM>(a.ls, apre, s.aw, kp[g], lj, tx[g], ty[g], s.x, s.y);
+                    if (lj == ks[g] || (CULL && far[g])) wgt = 0;    // l != k  (main_MIDASPOM.c:354)
+                    wd[g] = (double)wgt;
+                }
+                const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
+#pragma unroll
+                for (int t2 = 0; t2 < NYB / 2; t2++) {
+                    const double2 m = yb[t2];
+#pragma unroll
+                    for (int g = 0; g < TGT; g++) {
+                        acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
+                        acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
+                    }
+                }
+            };
+            if (warp_live) {
+                for (int sub = 0; sub < NTHR / 32; sub++) {          // warp-uniform: 32 sources against the warp's TGT target groups
+                    if (l0 + 32 * sub >= n) continue;
+                    if (CULL) {
+                        bool all_far = true;
+                        uint32_t nlive = 0;
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) {
+                            far[g] = reach_log2(gbox[g], a.box32[l0 / 32 + sub]) < thr[g];
+                            all_far = all_far && far[g]; nlive += !far[g] && gvalid[g];
+                        }
+                        if (all_far) continue;
+                        nexec += nlive;
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) nexec += gvalid[g];
+                    }
+#pragma unroll 2
+                    for (int j = 32 * sub; j < 32 * sub + 32; j++) source(j);
+                }
+            }
+            __syncthreads();
+            cur = nxt; stage ^= 1;
+        }
+#pragma unroll
+        for (int g = 0; g < TGT; g++) {
+            const int k = kp[g];
+            if (k >= 0) {
+#pragma unroll
+                for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = acc[g][t];
+            }
+        }
+    }
+    if (a.stats && lane == 0 && warp_live) {
+        int ngrp = 0;
+#pragma unroll
+        for (int g = 0; g < TGT; g++) ngrp += gvalid[g];
+        atomicAdd(&a.stats[MP_CNT_CONN_EXEC], (unsigned long long)nexec);
+        atomicAdd(&a.stats[MP_CNT_CONN_TOTAL], (unsigned long long)ngrp * (unsigned long long)((n + 31) / 32) * (unsigned long long)a.nwords);
+    }
+}
+
+}  // namespace mp

@@ -28,12 +28,16 @@ template <typename R> static int launch_area_weights(mp_engine *h, int set)
     CK(cudaGetLastError());
     return MP_OK;
 }
-static int launch_pack_y(mp_engine *h)
+// source records of k_conn (scan order; year bits + coordinates + area constant) for the parameter sets in set_mask
+template <typename R> static int launch_pack_sources(mp_engine *h, int set_mask)
 {
     Timed tm(h, MP_K_SMALL);
-    const int n = h->cfg.n_patches;
-    dim3 grid((n + 255) / 256, h->cfg.n_chains);
-    k_pack_y<<<grid, 256, 0, h->stream>>>(h->d_y, h->d_ybits, n, h->cfg.n_years - 1, h->nwords);
+    const int npad = conn_npad(h->cfg.n_patches);
+    dim3 grid((npad + 255) / 256, h->cfg.n_chains, h->nwords);
+    mp::Landscape<R> ls = view<R>(h);
+    if (h->geom != MP_GEOM_COORDS) { ls.px = nullptr; ls.py = nullptr; }
+    k_pack_sources<R><<<grid, 256, 0, h->stream>>>(ls, h->d_perm, (const R *)h->d_aw[0], (const R *)h->d_aw[1], h->d_y,
+                                                    h->cfg.n_years - 1, h->nwords, set_mask, (SrcRec<R> *)h->d_srec);
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -43,24 +47,28 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     ConnArgs<R> a;
     a.ls = view<R>(h);
     a.par[0] = h->d_par; a.par[1] = h->d_prop;
-    a.aw[0] = (const R *)h->d_aw[0]; a.aw[1] = (const R *)h->d_aw[1];
     a.S[0] = h->d_S[0]; a.S[1] = h->d_S[1];
-    a.ybits = h->d_ybits; a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords; a.set_base = set_base;
+    a.rec = (const SrcRec<R> *)h->d_srec;
+    a.ntrans = h->cfg.n_years - 1; a.nwords = h->nwords; a.nchains = h->cfg.n_chains; a.set_base = set_base;
     a.k_lo = h->conn_lo; a.k_hi = h->conn_hi < 0 ? h->cfg.n_patches : h->conn_hi;
     a.perm = h->d_perm; a.box32 = (const float4 *)h->d_tile_box;
+    a.mlow = h->d_mlow; a.area_max = (float)h->area_max; a.area_min = (float)h->area_min;   // bounds: launch_conn_bounds
+    a.stats = h->d_work;
     if (a.k_hi <= a.k_lo) return MP_OK;
-    dim3 grid((a.k_hi - a.k_lo + CONN_TILE * CONN_TGT - 1) / (CONN_TILE * CONN_TGT), h->cfg.n_chains, nsets);
     const int ny = a.ntrans;                          // year accumulators per target: next multiple of 4 (<= 32 per pass)
     // FP32 engines on landscapes with positions skip source tiles out of reach (see CONN_CULL_LOG2); FP64 never culls
     constexpr bool CAN_CULL = sizeof(R) == 4 && GEOM != MP_GEOM_DENSE;
     const bool cull = CAN_CULL && h->conn_cull && h->have_boxes;
-    // culled CTAs do unequal work: with fewer than ~4 of them per SM, one target per thread (twice the CTAs) balances better
-    a.mlow = h->d_mlow; a.area_max = (float)h->area_max; a.area_min = (float)h->area_min;   // bounds: launch_conn_bounds
-    const bool narrow = cull && (long long)grid.x * grid.y * grid.z < 4LL * h->sm_count;
-    if (narrow) grid.x = (a.k_hi - a.k_lo + CONN_TILE - 1) / CONN_TILE;
-#define MP_CONN(NYB) do { if (narrow) k_conn<R, GEOM, NYB, CAN_CULL, 1><<<grid, CONN_TILE, 0, h->stream>>>(a); \
-                          else if (cull) k_conn<R, GEOM, NYB, CAN_CULL><<<grid, CONN_TILE, 0, h->stream>>>(a); \
-                          else k_conn<R, GEOM, NYB, false><<<grid, CONN_TILE, 0, h->stream>>>(a); } while (0)
+    // CTA shape: 128 threads x 2 targets; with few CTAs per SM, 64 threads x 2 targets (twice the CTAs) balances the
+    // unequal (culled) work better.  MP_CONN_SHAPE=1|2 forces the wide | narrow shape.
+    const long long wide_ctas = (long long)((a.k_hi - a.k_lo + 255) / 256) * h->cfg.n_chains * nsets;
+    const bool narrow = h->conn_shape ? h->conn_shape == 2 : wide_ctas < 8LL * h->sm_count;
+    const int per_cta = narrow ? 128 : 256;
+    dim3 grid((a.k_hi - a.k_lo + per_cta - 1) / per_cta, h->cfg.n_chains, nsets);
+#define MP_CONN(NYB) do { if (narrow) { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, 64><<<grid, 64, 0, h->stream>>>(a);     \
+                                        else k_conn<R, GEOM, NYB, false, 2, 64><<<grid, 64, 0, h->stream>>>(a); }            \
+                          else { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, 128><<<grid, 128, 0, h->stream>>>(a);           \
+                                 else k_conn<R, GEOM, NYB, false, 2, 128><<<grid, 128, 0, h->stream>>>(a); } } while (0)
     if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
     else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);
 #undef MP_CONN
@@ -123,7 +131,7 @@ template <typename R, int GEOM> static int launch_sweep_y_g(mp_engine *h)
     const int nthr = (int)std::min<size_t>(NT, ((nN(h) + 31) / 32) * 32);
     kern<<<h->cfg.n_chains * (h->cfg.n_years - 1), nthr, smem, h->stream>>>(
         sampler_dev(h), h->sweep, view<R>(h), h->d_par, (const R *)h->d_aw[0], h->have_era ? h->d_era : nullptr, h->d_z,
-        h->d_y, h->d_S[0], h->cfg.n_years, (const int *)h->d_perm);
+        h->d_y, h->d_S[0], h->cfg.n_years, (const int *)h->d_perm, h->d_work);
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -167,10 +175,17 @@ static int launch_sweep_y_fast(mp_engine *h)
     // large landscapes: a cluster of 8 holds the task's state; with few tasks per GPU (year sharding) spread each
     // task over 16 SMs instead -- the scan is latency-bound per flip
     const int ntask_own = (C * ntrans - h->task_first + h->task_stride - 1) / h->task_stride;
-    const int cs = tpt > 1024 ? (h->fast_cs == 16 || (h->fast_cs == 0 && tpt >= 4096 && ntask_own * 16 <= h->sm_count) ? 16 : 8)
-                              : (h->fast_cs ? h->fast_cs : (tpt == 256 ? 1 : pick_cluster(C * ntrans, h->sm_count, 8)));
+    int cs = tpt > 1024 ? (h->fast_cs == 16 || (h->fast_cs == 0 && tpt >= 4096 && ntask_own * 16 <= h->sm_count) ? 16 : 8)
+                        : (h->fast_cs ? h->fast_cs : (tpt == 256 ? 1 : pick_cluster(C * ntrans, h->sm_count, 8)));
+    // a CTA holds 16 bytes per target of its share (+ the 2 KB record ring of the culled scan): widen the cluster until that fits
+    if (tpt >= 512 && tpt <= 1024) {
+        const size_t ept = (size_t)(n + tpt - 1) / tpt;
+        while (cs < 8 && ept * (size_t)(tpt / cs) * 16 + 2048 > 227 * 1024) cs *= 2;
+    }
     // exact spatial culling of the evaluation (mp_sweep_cull.cuh) where positions exist and the landscape is large
-    if (h->fast_cull && h->geom != MP_GEOM_DENSE && (tpt == 512 || tpt >= 2048))
+    const bool culled = h->fast_cull && h->geom != MP_GEOM_DENSE && (tpt == 512 || tpt >= 2048);
+    h->last_scan[0] = tpt; h->last_scan[1] = cs; h->last_scan[2] = culled ? (tpt > 1024 ? 4 : 2) : 1; h->last_scan[3] = culled;
+    if (culled)
         return h->geom == MP_GEOM_LINEAR ? mp_launch_sweep_cull_linear(h, cs, tpt) : mp_launch_sweep_cull_coords(h, cs, tpt);
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
@@ -205,8 +220,8 @@ template <typename R> static int launch_update_z(mp_engine *h)
 template <typename R> static int refresh_S(mp_engine *h)
 {
     int rc;
-    if ((rc = launch_pack_y(h)) != MP_OK) return rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
+    if ((rc = launch_pack_sources<R>(h, 1)) != MP_OK) return rc;
     if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
     const int rc2 = launch_conn<R>(h, 0, 1);
     if (rc2 == MP_OK) h->S_valid = true;
@@ -240,7 +255,6 @@ template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out
     const SamplerDev sd = sampler_dev(h);
     const bool do_ab = h->sc.sample_alpha || h->sc.sample_b;
     const bool sharded = h->conn_hi >= 0;
-    if ((rc = launch_pack_y(h)) != MP_OK) return rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
     if (do_ab) {
         { Timed tm(h, MP_K_SMALL);
@@ -251,6 +265,7 @@ template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out
     // The resident S is maintained by exact rank-1 updates; the FP32 engine recomputes it from scratch only
     // every MP_REFRESH_EVERY sweeps (the FP64 parity engine every sweep, like the CPU twin).
     const bool refresh = is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0 || !h->S_valid;
+    if (refresh || do_ab) if ((rc = launch_pack_sources<R>(h, (refresh ? 1 : 0) | (do_ab ? 2 : 0))) != MP_OK) return rc;
     if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
     if (sharded) {   // other ranks fill the other target columns: start from zeros so that a sum over ranks assembles S
         if (refresh) CK(cudaMemsetAsync(h->d_S[0], 0, nC(h) * ycells(h) * 8, h->stream));
@@ -379,8 +394,8 @@ int mp_destroy(mp_engine *h)
     drain_spans(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
-                     h->d_lsig, h->d_z, h->d_y, h->d_ybits, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_tile_box, h->d_mlow };
+                     h->d_lsig, h->d_z, h->d_y, h->d_srec, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_tile_box, h->d_mlow, h->d_work };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -413,6 +428,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     h->cfg = *cfg;
     if (const char *env = getenv("MP_FAST_CULL")) h->fast_cull = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_CULL")) h->conn_cull = atoi(env) != 0;
+    if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 2) h->conn_shape = v; }
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
@@ -434,7 +450,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_obs, T * N }, { (void **)&h->d_era, T }, { (void **)&h->d_par, C * sizeof(mp_params) },
         { (void **)&h->d_prop, C * sizeof(mp_params) }, { (void **)&h->d_lsig, C * MP_NLSIG * 8 },
         { (void **)&h->d_z, C * T * N }, { (void **)&h->d_y, C * (T - 1) * N },
-        { (void **)&h->d_ybits, C * h->nwords * N * 4 }, { (void **)&h->d_S[0], C * (T - 1) * N * 8 },
+        { &h->d_srec, 2 * C * h->nwords * (size_t)conn_npad((int)N) * (cfg->precision == MP_FP64 ? sizeof(SrcRec<double>) : sizeof(SrcRec<float>)) }, { (void **)&h->d_S[0], C * (T - 1) * N * 8 },
         { (void **)&h->d_S[1], C * (T - 1) * N * 8 }, { &h->d_aw[0], C * N * R }, { &h->d_aw[1], C * N * R },
         { (void **)&h->d_partial[0], C * MAX_COL_BLOCKS * 8 }, { (void **)&h->d_partial[1], C * MAX_COL_BLOCKS * 8 },
         { (void **)&h->d_llc, C * 8 }, { (void **)&h->d_logu, C * 8 }, { (void **)&h->d_ljac, C * 8 }, { (void **)&h->d_parts, C * MP_NPART * 8 },
@@ -443,12 +459,17 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
-        { (void **)&h->d_perm, N * sizeof(int) },
+        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_work, MP_CNT_N * sizeof(unsigned long long) },
         { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) }, { (void **)&h->d_mlow, C * ((N + 31) / 32) * sizeof(float) },
     };
     for (auto &r : reqs) {
         if ((e = cudaMalloc(r.p, r.bytes)) != cudaSuccess) return fail("cudaMalloc", e);
         if ((e = cudaMemset(*r.p, 0, r.bytes)) != cudaSuccess) return fail("cudaMemset", e);
+    }
+    {   // external-source distance units default to u_k = k + 1 (loss.c:365) until mp_set_source_units replaces them
+        std::vector<double> u(N);
+        for (size_t k = 0; k < N; k++) u[k] = (double)(k + 1);
+        if ((e = cudaMemcpy(h->d_src_unit, u.data(), N * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("memcpy", e);
     }
     // defaults: parameters of the reference's defaults (main_MIDASPOM.c:66-73), neutral variant terms
     std::vector<mp_params> par(C, mp_params{ 0.5, 0.5, 1.0 / 400.0, 0.0, 1.0, 1.0, 0.0, 0.0 });
@@ -866,6 +887,9 @@ int mp_set_shard(mp_engine *h, int conn_lo, int conn_hi, int task_first, int tas
     const int ntask = h->cfg.n_chains * (h->cfg.n_years - 1);
     REQUIRE(task_stride >= 1 && task_first >= 0 && task_first < std::max(ntask, 1) + task_stride, MP_ERR_ARG, "mp_set_shard: bad task subset");
     REQUIRE(conn_hi < 0 || (conn_lo >= 0 && conn_lo <= conn_hi && conn_hi <= h->cfg.n_patches), MP_ERR_ARG, "mp_set_shard: bad patch range");
+    // the culled k_conn takes its bounding boxes per 32-slot group and a CTA owns 256 targets: ranges must start on a CTA boundary
+    REQUIRE(conn_hi < 0 || (conn_lo % 256 == 0 && (conn_hi % 256 == 0 || conn_hi == h->cfg.n_patches)), MP_ERR_ARG,
+            "mp_set_shard: conn_lo and conn_hi must be multiples of 256 (conn_hi may also be n_patches)");
     h->conn_lo = conn_hi < 0 ? 0 : conn_lo; h->conn_hi = conn_hi; h->task_first = task_first; h->task_stride = task_stride;
     return MP_OK;
 }
@@ -1012,6 +1036,23 @@ int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset)
         if (launches) launches[i] = h->t_launch[i];
         if (reset) { h->t_ms[i] = 0.0; h->t_launch[i] = 0; }
     }
+    return MP_OK;
+}
+int mp_get_scan_geometry(mp_engine *h, int *out4)
+{
+    if (!h || !out4) return MP_ERR_ARG;
+    for (int i = 0; i < 4; i++) out4[i] = h->last_scan[i];
+    return MP_OK;
+}
+int mp_get_work_counters(mp_engine *h, uint64_t *out, int reset)
+{
+    if (!h || !out) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    unsigned long long dev[MP_CNT_N];
+    CK(cudaMemcpyAsync(dev, h->d_work, sizeof(dev), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < MP_CNT_N; i++) out[i] = (uint64_t)dev[i];
+    if (reset) CK(cudaMemsetAsync(h->d_work, 0, sizeof(dev), h->stream));
     return MP_OK;
 }
 int mp_probe_peaks(mp_engine *h, double *out4)

@@ -33,7 +33,7 @@ struct mp_engine {
     mp_params *d_par = nullptr, *d_prop = nullptr;
     double *d_lsig = nullptr;
     uint8_t *d_z = nullptr, *d_y = nullptr;
-    uint32_t *d_ybits = nullptr;
+    void *d_srec = nullptr;          // source records of k_conn (mp::SrcRec, [set][chain][word][padded slot], scan order)
     int nwords = 1;
     double *d_S[2] = { nullptr, nullptr };
     void *d_aw[2] = { nullptr, nullptr };
@@ -58,11 +58,14 @@ struct mp_engine {
     float *d_mlow = nullptr;                   // [chain][group] lower bound of S per group of 32 slots (k_group_min_S)
     double area_max = 1.0, area_min = 1.0;
     bool have_boxes = false; int conn_cull = 1;   // MP_CONN_CULL=0 disables the culling of k_conn
+    int conn_shape = 0;                        // CTA shape of k_conn: 0 choose, 1 = 128 threads x 2 targets, 2 = 64 x 2 (MP_CONN_SHAPE)
+    unsigned long long *d_work = nullptr;      // MP_CNT_* work counters (mp_get_work_counters)
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
     int *d_perm = nullptr;                     // scan (Morton) order of the patches: perm[slot] = patch
     int fast_cull = 1;               // exact spatial culling in the fast sweep (MP_FAST_CULL=0 disables)
     int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides
     int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
+    int last_scan[4] = { 0, 0, 0, 0 };   // geometry of the last y scan launched: threads per task, cluster size, candidates per trip, culled
     // timing
     bool timing = false;
     struct Span { cudaEvent_t a, b; int cat; };

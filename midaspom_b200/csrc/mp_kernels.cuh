@@ -1,8 +1,7 @@
 // mp_kernels.cuh -- the CUDA kernels of the SPOM engine (sm_100a).  Included by mp_engine.cu only.
 //
-//  k_pack_y        y bytes -> one 32-year bit word per (chain, patch)      (feeds k_conn)
+//  (mp_conn.cuh)   k_pack_sources, k_group_min_S, k_conn: the connectivity contraction
 //  k_area_weights  aw[set][chain][l] = A_l^b (FP64) or log2 A_l^b (FP32), see pair_weight
-//  k_conn          fused on-the-fly dispersal-kernel x occupancy contraction  (main_MIDASPOM.c:350-358)
 //  k_col_ll        colonisation log-terms + per-chain segmented reduction      (compPePc:40,44)
 //  k_counts        integer bookkeeping: extinction / detection / prior counts  (compPePc:38-39)
 //  k_flip_delta    rank-1 log-odds of one intermediate-state flip
@@ -12,31 +11,15 @@
 //  k_simulate      forward simulator (future.c:64-110)
 #pragma once
 #include "mp_device.cuh"
+#include "mp_conn.cuh"   // k_pack_sources, k_group_min_S, k_conn
 
 namespace mp {
 
-constexpr int CONN_TILE = 128;      // threads per CTA == sources per shared-memory tile
-constexpr int CONN_TGT = 2;         // targets per thread (register blocking of the year contraction)
 constexpr int COL_THREADS = 256;
 constexpr int MAX_COL_BLOCKS = 64;  // partial sums per chain (fixed => deterministic reduction order)
 constexpr int NCOUNT = 12;          // per-chain integer counters, see k_counts
 enum { CNT_N10 = 0, CNT_N10P = 1, CNT_N11 = 2, CNT_N11P = 3, CNT_BADEXT = 4, CNT_ND = 5, CNT_NM = 6,
        CNT_BADDET = 7, CNT_LAT1 = 8, CNT_LAT0 = 9, CNT_SY = 10, CNT_SZ = 11 };
-
-// ------------------------------------------------------------------ packing
-__global__ void k_pack_y(const uint8_t *__restrict__ y, uint32_t *__restrict__ ybits, int n, int ntrans, int nwords)
-{
-    const int c = blockIdx.y;
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n) return;
-    const uint8_t *yc = y + (size_t)c * ntrans * n;
-    for (int w = 0; w < nwords; w++) {
-        uint32_t bits = 0;
-        const int t1 = min(32, ntrans - 32 * w);
-        for (int t = 0; t < t1; t++) bits |= (uint32_t)(yc[(size_t)(32 * w + t) * n + l] != 0) << t;
-        ybits[((size_t)c * nwords + w) * n + l] = bits;
-    }
-}
 
 template <typename R>
 __global__ void k_area_weights(const mp_params *__restrict__ par, const double *__restrict__ area, R *__restrict__ aw, int n)
@@ -46,184 +29,6 @@ __global__ void k_area_weights(const mp_params *__restrict__ par, const double *
     if (l >= n) return;
     const double b = par[c].b;
     aw[(size_t)c * n + l] = area_pre<R>((area && b != 0.0) ? pow(area[l], b) : 1.0);
-}
-
-// ------------------------------------------------------------------ connectivity
-// One thread per target patch k, one CTA per (128 targets, chain, parameter set).  Sources are
-// staged 128 at a time in shared memory (coordinates, area weight, year bit word); the dispersal
-// weight is evaluated once per (target, source) pair and added to every year in which the source
-// is occupied.  Accumulation is FP64 in both precisions so that the later rank-1 downdates of
-// k_sweep_y cancel exactly.
-template <typename R> struct ConnArgs {
-    Landscape<R> ls;
-    const mp_params *par[2];
-    const R *aw[2];
-    double *S[2];
-    const uint32_t *ybits;
-    int ntrans, nwords;
-    int set_base;          // first parameter set of this launch (blockIdx.z counts from it)
-    int k_lo, k_hi;        // targets [k_lo, k_hi) of this launch (patch sharding over GPUs; whole range otherwise):
-                           // patch numbers, or scan-order slots for the culled variant
-    const int *perm;       // culled variant: scan-order slot -> patch (Morton order of planar landscapes)
-    const float4 *box32;   // culled variant: bounding box {xmin, xmax, ymin, ymax} of every group of 32 consecutive slots
-    const float *mlow;     // culled variant: [chain][group] lower bound of the group's S over all years (0 = unknown: no culling)
-    float area_max, area_min;   // extremes of the patch areas (1, 1 without areas): A_l^b <= max(area_max^b, area_min^b)
-};
-// Culled variant (FP32 engines, landscapes with positions): targets and sources are taken in scan (Morton) order, so
-// groups of 32 consecutive slots are spatially compact.  A group of 32 sources is skipped for a group of 32 targets
-// when every weight between them is below 2^-30 of the smallest S the target group currently has (k_group_min_S: the
-// resident S, any year), and a tile of 128 sources is not even loaded when that holds for all of the CTA's target
-// groups.  What is skipped is dominated by the sources just beyond the reach (2 pi R rho / alpha of them, a few
-// hundred at the benchmark density), i.e. ~1e-7 of S -- relative to each group's own S, so isolated patches with a
-// small S keep their accuracy.  Without a valid resident S (first sweep) mlow = 0 and nothing is skipped.  The FP64
-// parity engine never culls.
-constexpr float CONN_CULL_LOG2 = -30.f;
-
-// min over years and over the 32 patches of a scan-order group of the resident S (culling bound of k_conn)
-static __global__ void __launch_bounds__(32)
-k_group_min_S(const double *__restrict__ S, const int *__restrict__ perm, int n, int ntrans, int valid, float *__restrict__ mlow)
-{
-    const int g = blockIdx.x, c = blockIdx.y, slot = g * 32 + threadIdx.x, ngroups = gridDim.x;
-    float m = 3.0e38f;
-    if (valid && slot < n) {
-        const double *Sc = S + (size_t)c * ntrans * n + perm[slot];
-        for (int t = 0; t < ntrans; t++) m = fminf(m, (float)Sc[(size_t)t * n]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) mlow[(size_t)c * ngroups + g] = valid ? fmaxf(m * 0.999f, 0.f) : 0.f;
-}
-
-template <typename R, int GEOM, int NYB, bool CULL = false, int TGT = CONN_TGT>
-__global__ void __launch_bounds__(CONN_TILE) k_conn(ConnArgs<R> a)
-{
-    // Each thread owns TGT targets (k, k + 128, ...) and NYB year accumulators per target.
-    // Per source of the tile: coordinates, area constant, and the year bits expanded to 0.0 / 1.0
-    // doubles, so that the contraction over years is a chain of DFMAs
-    //   acc[t] = fma(w, y01[t], acc[t])   (== acc[t] + w or acc[t], exactly)
-    // fed by broadcast LDS.128; the y01 loads are shared by the TGT targets of the thread.
-    __shared__ R sx[CONN_TILE], sy[CONN_TILE], saw[CONN_TILE];
-    __shared__ uint32_t sbits[CONN_TILE];
-    __shared__ int sl[CULL ? CONN_TILE : 1];                          // culled variant: patch number of the tile's sources
-    __shared__ __align__(16) double sy01[CONN_TILE][NYB];
-    const int n = a.ls.n, c = blockIdx.y, set = blockIdx.z + a.set_base, tid = threadIdx.x;
-    // first target of the thread: patch kbase, then kbase + 128 (coalesced stores); in the culled variant scan-order
-    // slots kbase, kbase + 32, so that a warp owns 64 consecutive slots -- one spatially compact group
-    const int kstep = CULL ? 32 : CONN_TILE;
-    const int kbase = a.k_lo + blockIdx.x * CONN_TILE * TGT + (CULL ? (tid >> 5) * 32 * TGT + (tid & 31) : tid);
-    const mp_params *parp = set ? a.par[1] : a.par[0];
-    const R apre = alpha_pre<R>(parp[c].alpha);
-    const R *aw = (set ? a.aw[1] : a.aw[0]) + (size_t)c * n;
-    double *Sout = (set ? a.S[1] : a.S[0]) + (size_t)c * a.ntrans * n;
-    R tx[TGT], ty[TGT];
-    int kp[TGT];                                                 // patch number of the thread's targets (-1: none)
-#pragma unroll
-    for (int g = 0; g < TGT; g++) {
-        const int k = kbase + g * kstep;
-        kp[g] = k < a.k_hi ? (CULL ? a.perm[k] : k) : -1;
-        tx[g] = 0; ty[g] = 0;
-        if (GEOM == MP_GEOM_COORDS && kp[g] >= 0) { tx[g] = a.ls.px[kp[g]]; ty[g] = a.ls.py[kp[g]]; }
-    }
-    // boxes {xmin, xmax, ymin, ymax} of the CTA's targets and of the warp's targets (unions of 32-slot group boxes)
-    float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f), gbox[TGT];
-    auto box_union = [](const float4 &p, const float4 &q) { return make_float4(fminf(p.x, q.x), fmaxf(p.y, q.y), fminf(p.z, q.z), fmaxf(p.w, q.w)); };
-    // log2 of the largest distance factor exp(-alpha d) between two boxes (apre = -alpha log2 e), with a rounding margin
-    auto reach_log2 = [&](const float4 &p, const float4 &q) {
-        const float dx = fmaxf(0.f, fmaxf(q.x - p.y, p.x - q.y)), dy = fmaxf(0.f, fmaxf(q.z - p.w, p.z - q.w));
-        return (float)apre * (0.9999f * sqrtf(dx * dx + dy * dy));
-    };
-    // skip when log2(exp(-alpha d)) < thr: thr = CONN_CULL_LOG2 + log2(mlow / max_l A_l^b) of the target group(s); -inf = never
-    float thr_cta = 0.f, thr[TGT];
-    if (CULL) {
-        const int g0 = (a.k_lo + blockIdx.x * CONN_TILE * TGT) / 32, gend = (a.k_hi + 31) / 32, ngroups = (n + 31) / 32;
-        const float b = (float)parp[c].b;
-        const float law_max = fmaxf(b * log2f(a.area_max), b * log2f(a.area_min)) + 1e-3f;     // log2 of max_l A_l^b, rounded up
-        auto thr_of = [&](int g) { return CONN_CULL_LOG2 + log2f(a.mlow[(size_t)c * ngroups + g]) - law_max; };   // log2f(0) = -inf
-        tbox = a.box32[g0]; thr_cta = thr_of(g0);
-        for (int i = 1; i < CONN_TILE * TGT / 32; i++)
-            if (g0 + i < gend) { tbox = box_union(tbox, a.box32[g0 + i]); thr_cta = fminf(thr_cta, thr_of(g0 + i)); }
-        const int w0 = g0 + (tid >> 5) * TGT;
-#pragma unroll
-        for (int g = 0; g < TGT; g++) { gbox[g] = a.box32[min(w0 + g, gend - 1)]; thr[g] = thr_of(min(w0 + g, gend - 1)); }   // the warp's g-th group
-    }
-    for (int w = 0; w < a.nwords; w++) {
-        const uint32_t *bw = a.ybits + ((size_t)c * a.nwords + w) * n;
-        double acc[TGT][NYB];
-#pragma unroll
-        for (int g = 0; g < TGT; g++)
-#pragma unroll
-            for (int t = 0; t < NYB; t++) acc[g][t] = 0.0;
-        // one source of the tile against the thread's targets
-        bool far[TGT];                                                 // culled variant: group g is out of reach of the 32 sources at hand
-#pragma unroll
-        for (int g = 0; g < TGT; g++) far[g] = false;
-        auto source = [&](int l0, int j) {
-            if (sbits[j] == 0) return;                                 // tile-uniform: source empty in every year
-            double wd[TGT];
-            const int lj = CULL ? sl[j] : l0 + j;
-#pragma unroll
-            for (int g = 0; g < TGT; g++) {
-                R wgt = pair_weight<R, GEOM>(a.ls, apre, saw[j], kp[g], lj, tx[g], ty[g], sx[j], sy[j]);
-                if (lj == kp[g] || (CULL && far[g])) wgt = 0;           // l != k  (main_MIDASPOM.c:354)
-                wd[g] = (double)wgt;
-            }
-            const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
-#pragma unroll
-            for (int t2 = 0; t2 < NYB / 2; t2++) {
-                const double2 m = yb[t2];
-#pragma unroll
-                for (int g = 0; g < TGT; g++) {
-                    acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
-                    acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
-                }
-            }
-        };
-        for (int l0 = 0; l0 < n; l0 += CONN_TILE) {
-            if (CULL) {                                                // CTA-uniform: is any (target, source) pair of the tile within reach?
-                float4 sb = a.box32[l0 / 32];
-                for (int i = 1; i < CONN_TILE / 32; i++) if (l0 + 32 * i < n) sb = box_union(sb, a.box32[l0 / 32 + i]);
-                if (reach_log2(tbox, sb) < thr_cta) continue;
-            }
-            const int l = (CULL && l0 + tid < n) ? a.perm[l0 + tid] : l0 + tid;
-            uint32_t bits = 0;
-            if (l0 + tid < n) {
-                if (GEOM == MP_GEOM_COORDS) { sx[tid] = a.ls.px[l]; sy[tid] = a.ls.py[l]; }
-                saw[tid] = aw[l]; bits = bw[l];
-            }
-            if (CULL) sl[tid] = l;
-            sbits[tid] = bits;
-#pragma unroll
-            for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
-            __syncthreads();
-            if (kbase < a.k_hi) {
-                if (CULL) {
-                    for (int sub = 0; sub < CONN_TILE / 32; sub++) {   // warp-uniform: 32 sources against the warp's 64 targets
-                        // the decision is taken per (group of 32 targets, group of 32 sources): it does not depend on
-                        // how many groups a warp or a CTA holds, so every launch shape gives bit-identical sums
-                        if (l0 + 32 * sub >= n) continue;
-                        bool all_far = true;
-#pragma unroll
-                        for (int g = 0; g < TGT; g++) { far[g] = reach_log2(gbox[g], a.box32[l0 / 32 + sub]) < thr[g]; all_far = all_far && far[g]; }
-                        if (all_far) continue;
-#pragma unroll 2
-                        for (int j = 32 * sub; j < 32 * sub + 32; j++) source(l0, j);
-                    }
-                } else {
-#pragma unroll 2
-                    for (int j = 0; j < CONN_TILE; j++) source(l0, j);
-                }
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int g = 0; g < TGT; g++) {
-            const int k = kp[g];
-            if (k >= 0) {
-#pragma unroll
-                for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = acc[g][t];
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------ colonisation log-likelihood
@@ -644,7 +449,8 @@ template <typename R, int GEOM, int NT>
 __global__ void __launch_bounds__(NT, 1)
 k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
           const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S, int T,
-          const int *__restrict__ order /* visiting order of the scan: slot -> patch (oracle: spom_scan_order) */)
+          const int *__restrict__ order /* visiting order of the scan: slot -> patch (oracle: spom_scan_order) */,
+          unsigned long long *__restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, nthr = blockDim.x;
@@ -720,6 +526,7 @@ k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__res
     }
     __syncthreads();
     for (int q = tid; q < n; q += nthr) { St[q] = sS[q]; yt[q] = sF[q] & 1; }
+    if (stats && tid == 0) atomicAdd(&stats[MP_CNT_SCAN_DENSE], (unsigned long long)it * (unsigned long long)n);
 }
 
 // ------------------------------------------------------------------ forward simulator

@@ -35,15 +35,12 @@
 
 namespace mp {
 
-#ifdef MP_DEBUG_CULL
-__device__ unsigned long long g_cull_dbg[4];   // [0] warp-trips, [1] evaluated slots, [2] total slots, [3] committed slots
-#endif
-
 template <int GEOM, int CS, int TPT>
 __global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_params *__restrict__ par,
                const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
-               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order)
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order,
+               unsigned long long *__restrict__ stats /* MP_CNT_SCAN_* work counters of the engine (mp_get_work_counters) */)
 {
     static_assert(GEOM != MP_GEOM_DENSE, "culling needs positions");
     constexpr int NT = TPT / CS, NW = NT / 32, SP = TPT > 1024 ? MP_CULL_SPEC_LARGE : MP_CULL_SPEC;
@@ -124,6 +121,9 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     int nocc = count[2 * task + 1];
     const CandRec *recs = rec + (size_t)task * n;
     uint32_t uses[2] = { 0u, 0u };
+    // work counters of this warp (warp-uniform values, added to the engine's totals once at the end): trips, (candidate,
+    // 32-target group) evaluations executed, the part of them that belongs to retired candidates, groups committed
+    uint32_t st_trips = 0, st_exec = 0, st_ret = 0, st_commit = 0;
 
     // sums of SP per-thread values over the task's TPT threads (warp shuffles, then st.async of the warp or CTA
     // partials -- NV float4 per sender -- to every CTA of the cluster, completion counted on the destination's mbarrier)
@@ -251,9 +251,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             // groups where the weight exceeds 2^-36 min S: what is skipped stays far below the FP32 resolution of S even
             // when summed over every commit between two refreshes of S (at most 2^-36 x commits, in practice << 2^-30)
             uint32_t m = __ballot_sync(0xffffffffu, lane < ept && !(wub < 1.4551915e-11f * Gw));
-#ifdef MP_DEBUG_CULL
-            if (lane == 0) atomicAdd(&g_cull_dbg[3], (unsigned long long)__popc(m));
-#endif
+            st_commit += __popc(m);
             // B slots per trip: B independent (LDS, sqrt, ex2, two-sum, STS) chains, the loop is latency bound otherwise
             auto batch = [&](auto BB) {
                 constexpr int B = decltype(BB)::value;
@@ -336,9 +334,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             feel = feel || (c < nc && !zero[c] && !(wub[c] < 1.4886e-8f * Gw));
         }
         uint32_t m = __ballot_sync(0xffffffffu, lane < ept && feel);
-#ifdef MP_DEBUG_CULL
-        if (lane == 0) { atomicAdd(&g_cull_dbg[0], 1ull); atomicAdd(&g_cull_dbg[1], (unsigned long long)__popc(m)); atomicAdd(&g_cull_dbg[2], (unsigned long long)ept); }
-#endif
+        const uint32_t nfeel = __popc(m);
         float pd = 1.f;
         int cnt = 0;
         // B slots x SP candidates per trip: B * SP independent (sqrt, ex2, FFMA.SAT) chains
@@ -403,6 +399,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             }
         }
         i += adv;
+        st_trips++; st_exec += nfeel * (uint32_t)nc; st_ret += nfeel * (uint32_t)adv;
         // slide the window of bounds by adv
 #pragma unroll
         for (int aa = 1; aa <= SP; aa++)
@@ -419,6 +416,12 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             St[q] = fmax(((double)tq.x + (double)tq.y) - src_offset(q), 0.0);
             yt[q] = (uint8_t)((ybits >> j) & 1u);
         }
+    }
+    if (stats && lane == 0) {
+        atomicAdd(&stats[MP_CNT_SCAN_TRIPS], (unsigned long long)st_trips);
+        atomicAdd(&stats[MP_CNT_SCAN_EXEC], (unsigned long long)st_exec);
+        atomicAdd(&stats[MP_CNT_SCAN_RETIRED], (unsigned long long)st_ret);
+        atomicAdd(&stats[MP_CNT_SCAN_COMMIT], (unsigned long long)st_commit);
     }
     if (CS > 1) cluster_barrier();
 }
@@ -449,7 +452,8 @@ template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept)
     cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const int *)h->d_perm, (const mp_params *)h->d_par,
                           (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
-                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order));
+                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order,
+                          h->d_work));
     return MP_OK;
 }
 // culled variants exist for 512 threads per task (N up to 15,872) and the large-landscape geometries

@@ -174,7 +174,8 @@ template <int GEOM, int CS, int U, int TPT>
 __global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
 k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uint8_t *__restrict__ era,
                const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
-               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order)
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order,
+               unsigned long long *__restrict__ stats)
 {
     constexpr int NT = TPT / CS, NW = NT / 32;
     constexpr bool HIER = TPT / 32 > 32;                // more than 32 warps per task: reduce inside the CTA first
@@ -390,6 +391,7 @@ k_sweep_y_fast(Landscape<float> ls, const mp_params *__restrict__ par, const uin
             yt[q] = (uint8_t)((ybits >> j) & 1u);
         }
     }
+    if (stats && tid == 0 && rank == 0) atomicAdd(&stats[MP_CNT_SCAN_DENSE], (unsigned long long)ncand * (unsigned long long)n);
     if (CS > 1) cluster_barrier();                      // no CTA leaves while a peer could still address its smem
 }
 
@@ -421,7 +423,8 @@ template <int CS, int U, int TPT> static int launch_fast(mp_engine *h, int ept)
     cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const mp_params *)h->d_par,
                           (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
-                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order));
+                          (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order,
+                          h->d_work));
     return MP_OK;
 }
 template <int CS, int TPT> static int launch_fast_u(mp_engine *h, int ept)

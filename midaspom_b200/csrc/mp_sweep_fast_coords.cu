@@ -6,6 +6,3 @@
 #include "mp_sweep_cull.cuh"
 int mp_launch_sweep_fast_coords(mp_engine *h, int cs, int tpt) { return mp::launch_fast_any(h, cs, tpt); }
 int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt) { return mp::launch_cull_any(h, cs, tpt); }
-#ifdef MP_DEBUG_CULL
-extern "C" int mp_debug_cull_counters(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, mp::g_cull_dbg, 32); }
-#endif

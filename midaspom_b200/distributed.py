@@ -127,6 +127,14 @@ class ShardedChain:
         self.reduce_fn = reduce_fn
         self.torch = torch
 
+    def describe(self):
+        return (f"one chain over {self.world} GPUs: connectivity by target patches, y scan by years, "
+                "all-reduce of S and y per sweep (NCCL through torch.distributed)")
+
+    def bytes_per_sweep(self):
+        C, T, N = self.eng.C, self.eng.T, self.eng.N
+        return 2 * C * (T - 1) * N * 8 + C * (T - 1) * N + (C * (T - 1) * N * 8) / 16   # S_prop + S + y every sweep; refresh of S / 16
+
     def phase_a(self):
         flags = self.eng.sweep_phase(PH_PROPOSE_CONN)
         self.eng.synchronize()

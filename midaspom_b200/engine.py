@@ -18,6 +18,7 @@ FP32, FP64 = 0, 1
 GEOM_LINEAR, GEOM_COORDS, GEOM_DENSE = 0, 1, 2
 NDRAW, NLSIG, NPART = 11, 8, 4
 KERNEL_CATEGORIES = ("conn", "col", "sweep_y", "sweep_z", "small", "sim")
+WORK_COUNTERS = ("scan_trips", "scan_exec", "scan_retired", "scan_commit", "scan_dense", "conn_exec", "conn_total", "gemm_tiles")
 DRAW_FIELDS = ("e", "c", "alpha", "b", "p", "loglik", "n_y1", "n_z1", "K", "Ksrc", "dsrc")
 
 # every symbol include/libmidaspom_cuda.h declares
@@ -29,7 +30,7 @@ ABI_SYMBOLS = (
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
     "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
-    "mp_get_scan_order",
+    "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry",
 )
 
 
@@ -119,6 +120,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_set_timing.argtypes = [vp, C.c_int]
     L.mp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
     L.mp_probe_peaks.argtypes = [vp, dp]
+    L.mp_get_work_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
+    L.mp_get_scan_geometry.argtypes = [vp, C.POINTER(C.c_int)]
     L.mp_exact_posterior.argtypes = [C.c_int, i8p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                      C.c_double, C.c_double, dp, dp, C.POINTER(C.c_int)]
     L.mp_exact_last_error.restype = C.c_char_p
@@ -377,6 +380,17 @@ class Engine:
         launches = np.zeros(len(KERNEL_CATEGORIES), dtype=np.int64)
         self._ck(self.lib.mp_get_timing(self.h, _p(ms, _dp), _p(launches, C.POINTER(C.c_int64)), int(reset)), "mp_get_timing")
         return dict(zip(KERNEL_CATEGORIES, ms.tolist())), dict(zip(KERNEL_CATEGORIES, launches.tolist()))
+
+    def work_counters(self, reset=False):
+        """Work executed by the hot kernels since the last reset (mp_get_work_counters)."""
+        out = (C.c_uint64 * len(WORK_COUNTERS))()
+        self._ck(self.lib.mp_get_work_counters(self.h, out, int(reset)), "mp_get_work_counters")
+        return dict(zip(WORK_COUNTERS, [int(v) for v in out]))
+
+    def scan_geometry(self):
+        out = (C.c_int * 4)()
+        self._ck(self.lib.mp_get_scan_geometry(self.h, out), "mp_get_scan_geometry")
+        return dict(threads_per_task=out[0], cluster=out[1], candidates_per_trip=out[2], culled=bool(out[3]))
 
     def probe_peaks(self):
         out = np.zeros(4)

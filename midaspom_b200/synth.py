@@ -14,7 +14,7 @@ import numpy as np
 WORKLOADS = {
     # name: (N patches, T years, chains per GPU, imperfect detection)
     "cfg2": dict(n=1000, T=10, chains_per_gpu=8, detect=1, desc="synthetic N=1,000 x T=10, 8 chains, imperfect detection"),
-    "cfg3": dict(n=10000, T=20, chains_per_gpu=8, detect=0, desc="synthetic N=10,000 x T=20, 64 chains over 8 GPUs (8 per GPU)"),
+    "cfg3": dict(n=10000, T=20, chains_per_gpu=8, chains_total=64, detect=0, desc="synthetic N=10,000 x T=20, 64 independent chains sharded over the GPUs"),
     "cfg4": dict(n=10000, T=20, chains_per_gpu=8, detect=0, era_pre=10, K=3.0,
                  desc="synthetic N=10,000 x T=20, 8 chains per GPU, die-off variant: first 10 transitions pre-event with K_D=3 (E=e/K, C=c K S), K sampled"),
     "cfg4l": dict(n=10000, T=20, chains_per_gpu=8, detect=0, era_pre=10, Ksrc=5.0, dsrc=500.0,
@@ -77,11 +77,11 @@ def make_workload_large(name: str, seed: int = 12345, device: int = 0):
                 chains_per_gpu=w["chains_per_gpu"], desc=w["desc"])
 
 
-def make_workload(name: str, seed: int = 12345):
+def make_workload(name: str, seed: int = 12345, device: int = 0):
     w = WORKLOADS[name]
     n, T = w["n"], w["T"]
     if n > 20000:
-        return make_workload_large(name, seed)
+        return make_workload_large(name, seed, device)
     rng = np.random.default_rng(seed)
     side = np.sqrt(n) * 250.0
     px, py = rng.uniform(0, side, n), rng.uniform(0, side, n)
@@ -121,6 +121,8 @@ def make_workload(name: str, seed: int = 12345):
     truth = dict(e=e, c=c, alpha=alpha, b=b, p=TRUTH["p_detect"] if w["detect"] else 1.0)
     out = dict(name=name, n=n, T=T, px=px, py=py, area=area, obs=obs, z_true=z, truth=truth, detect=w["detect"],
                chains_per_gpu=w["chains_per_gpu"], desc=w["desc"])
+    if "chains_total" in w:
+        out["chains_total"] = w["chains_total"]
     if era_pre:
         out["era"] = (np.arange(T - 1) < era_pre).astype(np.uint8)
         truth["K"] = Kv

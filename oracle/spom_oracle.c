@@ -139,6 +139,19 @@ void spom_connectivity(const spom_model *m, double alpha, double b, const uint8_
         S[k] = s;
     }
 }
+/* the same sum for a list of target patches only (O(ntargets * n): checks of very large landscapes on a sample) */
+void spom_connectivity_targets(const spom_model *m, double alpha, double b, const uint8_t *y, const int32_t *targets,
+                               int ntargets, double *S)
+{
+    const int n = m->n;
+    for (int i = 0; i < ntargets; i++) {
+        const int k = targets[i];
+        double s = 0.0;
+        for (int l = 0; l < n; l++)
+            if (l != k && y[l]) s += spom_weight(m, alpha, b, k, l);
+        S[i] = s;
+    }
+}
 /* loss.c:365  M[n][j]=exp(-a*(j+1)*d_L) ; future.c:277 likewise with the -s distance */
 double spom_source_term(const spom_model *m, const spom_params *p, int k)
 {

@@ -80,6 +80,8 @@ void   spom_scan_order(const spom_model *m, int32_t *order);
 /* ---- likelihood pieces ---- */
 double spom_weight(const spom_model *m, double alpha, double b, int target, int source);
 void   spom_connectivity(const spom_model *m, double alpha, double b, const uint8_t *y_row, double *S_row);
+void   spom_connectivity_targets(const spom_model *m, double alpha, double b, const uint8_t *y_row,
+                                 const int32_t *targets, int ntargets, double *S_out /* ntargets */);
 double spom_source_term(const spom_model *m, const spom_params *p, int k);
 /* returns Pe*Pc; pe_out / pc_out (nullable) receive the two factors (Pee / Pcc entries of compPePc) */
 double spom_transition_prob(const spom_model *m, const spom_params *p, int pre_event,

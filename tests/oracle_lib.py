@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         L.spom_u01.argtypes = [C.c_uint32]; L.spom_u01.restype = C.c_double
         L.spom_weight.argtypes = [mp, C.c_double, C.c_double, C.c_int, C.c_int]; L.spom_weight.restype = C.c_double
         L.spom_connectivity.argtypes = [mp, C.c_double, C.c_double, _u8p, _dp]
+        L.spom_connectivity_targets.argtypes = [mp, C.c_double, C.c_double, _u8p, C.POINTER(C.c_int32), C.c_int, _dp]
         L.spom_source_term.argtypes = [mp, pp, C.c_int]; L.spom_source_term.restype = C.c_double
         L.spom_transition_prob.argtypes = [mp, pp, C.c_int, _u8p, _u8p, _u8p, _dp, _dp]
         L.spom_transition_prob.restype = C.c_double
@@ -138,6 +139,16 @@ def connectivity(m: Model, alpha, b, y_row):
     y_row = u8(y_row)
     S = np.zeros(m.n)
     lib().spom_connectivity(m.ref(), alpha, b, _ptr(y_row, _u8p), _ptr(S, _dp))
+    return S
+
+
+def connectivity_targets(m: Model, alpha, b, y_row, targets):
+    """S of the listed target patches only (same sum, same order as spom_connectivity)."""
+    y_row = u8(y_row)
+    targets = np.ascontiguousarray(targets, dtype=np.int32)
+    S = np.zeros(len(targets))
+    lib().spom_connectivity_targets(m.ref(), alpha, b, _ptr(y_row, _u8p), targets.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    len(targets), _ptr(S, _dp))
     return S
 
 
