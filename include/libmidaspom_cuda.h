@@ -190,6 +190,10 @@ int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset);
 enum { MP_CNT_SCAN_TRIPS = 0, MP_CNT_SCAN_EXEC = 1, MP_CNT_SCAN_RETIRED = 2, MP_CNT_SCAN_COMMIT = 3, MP_CNT_SCAN_DENSE = 4,
        MP_CNT_CONN_EXEC = 5, MP_CNT_CONN_TOTAL = 6, MP_CNT_GEMM_TILES = 7, MP_CNT_N = 8 };
 int mp_get_work_counters(mp_engine *h, uint64_t *out /* MP_CNT_N */, int reset);
+/* which kernel evaluated the connectivity last: 0 = k_conn (per-chain parameters, FP64 accumulation), 1 = the tensor-core
+ * contraction k_conn_gemm (FP32 engines; taken by mp_connectivity / mp_loglik / mp_loglik_host when every chain holds the
+ * same alpha and b as uploaded by mp_set_params, the matrix form c*M%*%pti of Rscript/simuls_traj.R:16,203,214) */
+int mp_get_conn_path(mp_engine *h);
 /* launch geometry of the last y scan: out4 = threads per (chain, year) task, CTAs per cluster, candidates evaluated per
  * trip (1 + speculative), 1 if the spatially culled kernel ran (0: k_sweep_y_fast; all 0: the generic FP64 k_sweep_y) */
 int mp_get_scan_geometry(mp_engine *h, int *out4);

@@ -15,6 +15,7 @@
 
 namespace mp {
 
+constexpr int CONN_BATCH = 4;      // sources whose weights are evaluated together before their year contractions
 constexpr int CONN_PAD = 128;       // the record stream of a (set, chain, word) is padded to whole tiles (zero records)
 
 template <typename R> struct SrcRec;
@@ -132,14 +133,15 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
     const R apre = alpha_pre<R>(parp[c].alpha);
     double *Sout = (set ? a.S[1] : a.S[0]) + (size_t)c * a.ntrans * n;
     R tx[TGT], ty[TGT];
-    int ks[TGT], kp[TGT];                                            // slot and patch number of the thread's targets (-1: none)
+    int ks[TGT], kp[TGT], kq[TGT];                                   // slot and patch number of the thread's targets (-1: none); patch used in the arithmetic
 #pragma unroll
     for (int g = 0; g < TGT; g++) {
         const int k = kbase + g * 32;
         ks[g] = k < a.k_hi ? k : -1;
         kp[g] = k < a.k_hi ? a.perm[k] : -1;
+        kq[g] = a.perm[min(k, a.k_hi - 1)];                          // a thread without a target evaluates the last one (branch-free; never stored)
         tx[g] = 0; ty[g] = 0;
-        if (GEOM == MP_GEOM_COORDS && kp[g] >= 0) { tx[g] = a.ls.px[kp[g]]; ty[g] = a.ls.py[kp[g]]; }
+        if (GEOM == MP_GEOM_COORDS) { tx[g] = a.ls.px[kq[g]]; ty[g] = a.ls.py[kq[g]]; }
     }
     if (tid == 0) {
         conn_mbar_init(conn_smem_u32(&full[0]), 1); conn_mbar_init(conn_smem_u32(&full[1]), 1);
@@ -217,27 +219,32 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
             }
             __syncthreads();
             const int l0 = cur * NTHR;
-            // one source of the tile against the thread's targets
-            auto source = [&](int j) {
-                const SrcRec<R> s = sr[j];                           // broadcast LDS.128
-                if (s.bits == 0) return;                             // tile-uniform: source empty in every year of this word
-                double wd[TGT];
-                const int lj = l0 + j;                               // slot of the source (== patch number without coordinates)
+            // CONN_BATCH sources at a time: first all their weights (independent SQRT / EX2 chains that overlap), then the
+            // year contraction of each -- the weight latency is paid once per batch, not once per source
+            auto batch = [&](int j0) {
+                double wd[CONN_BATCH][TGT];
 #pragma unroll
-                for (int g = 0; g < TGT; g++) {
-                    if (ks[g] < 0) { wd[g] = 0.0; continue; }        // no target: nothing to address (dense: dist[source * n + target])
-                    R wgt = pair_weight<R, GEOM>(a.ls, apre, s.aw, kp[g], lj, tx[g], ty[g], s.x, s.y);
-                    if (lj == ks[g] || (CULL && far[g])) wgt = 0;    // l != k  (main_MIDASPOM.c:354)
-                    wd[g] = (double)wgt;
-                }
-                const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j][0]);
-#pragma unroll
-                for (int t2 = 0; t2 < NYB / 2; t2++) {
-                    const double2 m = yb[t2];
+                for (int u = 0; u < CONN_BATCH; u++) {
+                    const SrcRec<R> s = sr[j0 + u];                  // broadcast LDS.128
+                    const int lj = l0 + j0 + u;                      // slot of the source (== patch number without coordinates)
 #pragma unroll
                     for (int g = 0; g < TGT; g++) {
-                        acc[g][2 * t2] = fma(wd[g], m.x, acc[g][2 * t2]);
-                        acc[g][2 * t2 + 1] = fma(wd[g], m.y, acc[g][2 * t2 + 1]);
+                        R wgt = pair_weight<R, GEOM>(a.ls, apre, s.aw, kq[g], lj, tx[g], ty[g], s.x, s.y);
+                        if (lj == ks[g] || (CULL && far[g])) wgt = 0;    // l != k  (main_MIDASPOM.c:354)
+                        wd[u][g] = (double)wgt;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CONN_BATCH; u++) {
+                    const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j0 + u][0]);
+#pragma unroll
+                    for (int t2 = 0; t2 < NYB / 2; t2++) {
+                        const double2 m = yb[t2];
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) {
+                            acc[g][2 * t2] = fma(wd[u][g], m.x, acc[g][2 * t2]);
+                            acc[g][2 * t2 + 1] = fma(wd[u][g], m.y, acc[g][2 * t2 + 1]);
+                        }
                     }
                 }
             };
@@ -258,8 +265,8 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
 #pragma unroll
                         for (int g = 0; g < TGT; g++) nexec += gvalid[g];
                     }
-#pragma unroll 2
-                    for (int j = 32 * sub; j < 32 * sub + 32; j++) source(j);
+#pragma unroll 1
+                    for (int j = 32 * sub; j < 32 * sub + 32; j += CONN_BATCH) batch(j);
                 }
             }
             __syncthreads();

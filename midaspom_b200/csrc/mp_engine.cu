@@ -216,11 +216,26 @@ template <typename R> static int launch_update_z(mp_engine *h)
     return MP_OK;
 }
 
+// every chain holds the same (alpha, b), known on the host: the connectivity is one dense contraction (mp_conn_gemm.cu)
+static bool gemm_eligible(const mp_engine *h)
+{
+    if (is64(h) || !h->use_gemm || h->geom == MP_GEOM_DENSE || h->conn_hi >= 0 || !h->par_host_valid) return false;
+    if (h->cfg.n_patches < h->gemm_min_n || h->par_host.size() != nC(h)) return false;
+    for (size_t c = 1; c < nC(h); c++)
+        if (h->par_host[c].alpha != h->par_host[0].alpha || h->par_host[c].b != h->par_host[0].b) return false;
+    return true;
+}
 // recompute S (set 0) from the resident y and parameters
 template <typename R> static int refresh_S(mp_engine *h)
 {
     int rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
+    if (gemm_eligible(h)) {
+        if ((rc = mp_launch_conn_gemm(h, h->par_host[0].alpha)) != MP_OK) return rc;
+        h->S_valid = true; h->last_conn_path = 1;
+        return MP_OK;
+    }
+    h->last_conn_path = 0;
     if ((rc = launch_pack_sources<R>(h, 1)) != MP_OK) return rc;
     if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
     const int rc2 = launch_conn<R>(h, 0, 1);
@@ -395,7 +410,7 @@ int mp_destroy(mp_engine *h)
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_srec, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_tile_box, h->d_mlow, h->d_work };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_tile_box, h->d_mlow, h->d_work, h->d_gemm };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -428,6 +443,8 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     h->cfg = *cfg;
     if (const char *env = getenv("MP_FAST_CULL")) h->fast_cull = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_CULL")) h->conn_cull = atoi(env) != 0;
+    if (const char *env = getenv("MP_CONN_GEMM")) h->use_gemm = atoi(env) != 0;
+    if (const char *env = getenv("MP_CONN_GEMM_MIN_N")) { const int v = atoi(env); if (v >= 1) h->gemm_min_n = v; }
     if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 2) h->conn_shape = v; }
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
@@ -645,6 +662,7 @@ int mp_set_params(mp_engine *h, const mp_params *par)
     for (size_t c = 0; c < nC(h); c++) REQUIRE(par[c].K > 0.0 && par[c].alpha > 0.0, MP_ERR_ARG, "need K > 0 and alpha > 0");
     h->any_src = false; h->S_valid = false;
     for (size_t c = 0; c < nC(h); c++) if (par[c].Ksrc != 0.0) h->any_src = true;
+    h->par_host.assign(par, par + nC(h)); h->par_host_valid = true;
     CK(cudaMemcpyAsync(h->d_par, par, nC(h) * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return MP_OK;
@@ -874,6 +892,7 @@ int mp_sweep(mp_engine *h, int nsweeps)
     int rc = check_ready(h);
     if (rc != MP_OK) return rc;
     REQUIRE(h->have_sc && h->have_obs, MP_ERR_STATE, "sampler not configured (mp_init_chains / mp_set_sampler)");
+    h->par_host_valid = false;                           // the sampler moves the parameters on the device
     for (int s = 0; s < nsweeps; s++) {
         rc = is64(h) ? sweep_once<double>(h) : sweep_once<float>(h);
         if (rc != MP_OK) return rc;
@@ -901,6 +920,7 @@ int mp_sweep_phase(mp_engine *h, int phase, int *flags_out)
     if (rc != MP_OK) return rc;
     REQUIRE(h->have_sc && h->have_obs, MP_ERR_STATE, "sampler not configured (mp_init_chains / mp_set_sampler)");
     REQUIRE(!is64(h) || (h->conn_hi < 0 && h->task_stride == 1), MP_ERR_UNSUPPORTED, "sharded phases need the FP32 engine");
+    h->par_host_valid = false;
     switch (phase) {
     case PH_PROPOSE_CONN: return is64(h) ? phase_propose_conn<double>(h, flags_out) : phase_propose_conn<float>(h, flags_out);
     case PH_DECIDE_Z: return is64(h) ? phase_decide_z<double>(h) : phase_decide_z<float>(h);
@@ -1038,6 +1058,7 @@ int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset)
     }
     return MP_OK;
 }
+int mp_get_conn_path(mp_engine *h) { return h ? h->last_conn_path : MP_ERR_ARG; }
 int mp_get_scan_geometry(mp_engine *h, int *out4)
 {
     if (!h || !out4) return MP_ERR_ARG;

@@ -58,6 +58,11 @@ struct mp_engine {
     float *d_mlow = nullptr;                   // [chain][group] lower bound of S per group of 32 slots (k_group_min_S)
     double area_max = 1.0, area_min = 1.0;
     bool have_boxes = false; int conn_cull = 1;   // MP_CONN_CULL=0 disables the culling of k_conn
+    void *d_gemm = nullptr; size_t gemm_bytes = 0;   // BF16 occupancy columns + source records of the tensor-core path (mp_conn_gemm.cu)
+    std::vector<mp_params> par_host;           // parameters as last uploaded by mp_set_params ...
+    bool par_host_valid = false;               // ... still what the device holds (the sampler changes them on the device)
+    int use_gemm = 1, gemm_min_n = 1024;       // tensor-core connectivity for chains sharing (alpha, b): MP_CONN_GEMM=0 disables, MP_CONN_GEMM_MIN_N
+    int last_conn_path = 0;                    // 0: k_conn, 1: k_conn_gemm (mp_get_conn_path)
     int conn_shape = 0;                        // CTA shape of k_conn: 0 choose, 1 = 128 threads x 2 targets, 2 = 64 x 2 (MP_CONN_SHAPE)
     unsigned long long *d_work = nullptr;      // MP_CNT_* work counters (mp_get_work_counters)
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
@@ -142,3 +147,5 @@ int mp_launch_sweep_fast_coords(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_fast_dense(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_cull_linear(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt);
+// tensor-core connectivity of every chain with one (alpha, b) (mp_conn_gemm.cu)
+int mp_launch_conn_gemm(mp_engine *h, double alpha);

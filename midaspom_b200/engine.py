@@ -30,7 +30,7 @@ ABI_SYMBOLS = (
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
     "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
-    "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry",
+    "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry", "mp_get_conn_path",
 )
 
 
@@ -122,6 +122,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_probe_peaks.argtypes = [vp, dp]
     L.mp_get_work_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     L.mp_get_scan_geometry.argtypes = [vp, C.POINTER(C.c_int)]
+    L.mp_get_conn_path.argtypes = [vp]
     L.mp_exact_posterior.argtypes = [C.c_int, i8p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                      C.c_double, C.c_double, dp, dp, C.POINTER(C.c_int)]
     L.mp_exact_last_error.restype = C.c_char_p
@@ -386,6 +387,10 @@ class Engine:
         out = (C.c_uint64 * len(WORK_COUNTERS))()
         self._ck(self.lib.mp_get_work_counters(self.h, out, int(reset)), "mp_get_work_counters")
         return dict(zip(WORK_COUNTERS, [int(v) for v in out]))
+
+    def conn_path(self):
+        """Kernel that evaluated the connectivity last: "k_conn" or "gemm" (tcgen05 contraction for chains sharing alpha, b)."""
+        return ("k_conn", "gemm")[self.lib.mp_get_conn_path(self.h)]
 
     def scan_geometry(self):
         out = (C.c_int * 4)()

@@ -100,10 +100,11 @@ def test_connectivity_at_cfg5_on_sampled_targets(precision):
         eng.set_state(z[None], y[None])
         if precision == mb.FP64:
             # the FP64 parity engine never culls: evaluate a target range only (the patch-sharding knob), sample inside it
+            # (a range of scan-order slots on landscapes with positions: mp_set_shard)
             lo, hi = 25600, 25600 + 2560
             eng.set_shard(lo, hi, 0, 1)
             S = eng.connectivity()[0]
-            targets = np.sort(rng.choice(np.arange(lo, hi), 256, replace=False)).astype(np.int32)
+            targets = np.sort(rng.choice(eng.scan_order()[lo:hi], 256, replace=False)).astype(np.int32)
             checks = [("fp64", S)]
         else:
             S1 = eng.connectivity()[0]
