@@ -398,6 +398,20 @@ def run_ours(args, rank, local_rank, world):
     ess_min = min((v["ess"] for v in summ.values()), default=float("nan"))
     z, y = eng.get_state()
     ncand = float(((z[:, :-1] & z[:, 1:]) == 1).sum()) / cpg             # candidate cells per chain-sweep
+    # the same evaluation for a batch of chains that share (alpha, b): the connectivity is one dense contraction and runs on the
+    # tensor cores (k_conn_gemm: tcgen05.mma + TMEM + TMA); every chain gets chain 0's current parameters
+    p0 = eng.get_params()[0]
+    eng.set_params([p0] * cpg)
+    eng.connectivity(fetch=False); eng.loglik()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_ll):
+        eng.connectivity(fetch=False)
+        eng.loglik()
+    barrier()
+    (t_ll_g,) = max_over_ranks([time.perf_counter() - t0])
+    lik_evals_shared = dict(value=chains_total * n_ll / t_ll_g, connectivity_kernel=eng.conn_path(),
+                            note="all chains of a GPU hold the same (alpha, b): fixed-parameter batch evaluation")
     probe = eng.probe_peaks() if rank == 0 else None
     eng.close()
     del arm
@@ -446,7 +460,7 @@ def run_ours(args, rank, local_rank, world):
                     kernel_ms={k: round(v, 4) for k, v in kms.items()}, kernel_launches=klaunch,
                     kernel_split_note=f"separate pass of {K} steps with per-kernel CUDA events on ({split_total / K:.3f} ms per step); `value` is timed with them off",
                     wall_s_timed_region=t_wall,
-                    likelihood_evals_per_sec=lik_evals,
+                    likelihood_evals_per_sec=lik_evals, likelihood_evals_per_sec_shared_params=lik_evals_shared,
                     ess_per_sec=ess_min / run_s if run_s > 0 else None,
                     ess=dict(min_ess=ess_min, seconds=run_s, sweeps=(n_ess // 2 if ess_run is not None else nd - W),
                              note="min over sampled parameters of the summed per-chain ESS (Geyer), second half of a separate "

@@ -59,19 +59,20 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     // FP32 engines on landscapes with positions skip source tiles out of reach (see CONN_CULL_LOG2); FP64 never culls
     constexpr bool CAN_CULL = sizeof(R) == 4 && GEOM != MP_GEOM_DENSE;
     const bool cull = CAN_CULL && h->conn_cull && h->have_boxes;
-    // CTA shape: 128 threads x 2 targets; with few CTAs per SM, 64 threads x 2 targets (twice the CTAs) balances the
-    // unequal (culled) work better.  MP_CONN_SHAPE=1|2 forces the wide | narrow shape.
+    // CTA shape: 128 threads x 2 targets; with few CTAs per SM, 64 or 32 threads x 2 targets (2x / 4x the CTAs) balance the
+    // unequal (culled) work better.  MP_CONN_SHAPE=1|2|3 forces a shape.
     const long long wide_ctas = (long long)((a.k_hi - a.k_lo + 255) / 256) * h->cfg.n_chains * nsets;
-    const bool narrow = h->conn_shape ? h->conn_shape == 2 : wide_ctas < 8LL * h->sm_count;
-    const int per_cta = narrow ? 128 : 256;
+    // shape 1: 128 threads, 2: 64 threads, 3: 32 threads (2 targets per thread each)
+    const int shape = h->conn_shape ? h->conn_shape : wide_ctas >= 16LL * h->sm_count ? 1 : wide_ctas >= 4LL * h->sm_count ? 2 : 3;
+    const int per_cta = shape == 1 ? 256 : shape == 2 ? 128 : 64;
     dim3 grid((a.k_hi - a.k_lo + per_cta - 1) / per_cta, h->cfg.n_chains, nsets);
-#define MP_CONN(NYB) do { if (narrow) { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, 64><<<grid, 64, 0, h->stream>>>(a);     \
-                                        else k_conn<R, GEOM, NYB, false, 2, 64><<<grid, 64, 0, h->stream>>>(a); }            \
-                          else { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, 128><<<grid, 128, 0, h->stream>>>(a);           \
-                                 else k_conn<R, GEOM, NYB, false, 2, 128><<<grid, 128, 0, h->stream>>>(a); } } while (0)
+#define MP_CONN_T(NYB, NT) do { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, NT><<<grid, NT, 0, h->stream>>>(a);      \
+                                else k_conn<R, GEOM, NYB, false, 2, NT><<<grid, NT, 0, h->stream>>>(a); } while (0)
+#define MP_CONN(NYB) do { if (shape == 1) MP_CONN_T(NYB, 128); else if (shape == 2) MP_CONN_T(NYB, 64); else MP_CONN_T(NYB, 32); } while (0)
     if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
     else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);
 #undef MP_CONN
+#undef MP_CONN_T
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -226,11 +227,11 @@ static bool gemm_eligible(const mp_engine *h)
     return true;
 }
 // recompute S (set 0) from the resident y and parameters
-template <typename R> static int refresh_S(mp_engine *h)
+template <typename R> static int refresh_S(mp_engine *h, bool allow_gemm = true)
 {
     int rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
-    if (gemm_eligible(h)) {
+    if (allow_gemm && gemm_eligible(h)) {
         if ((rc = mp_launch_conn_gemm(h, h->par_host[0].alpha)) != MP_OK) return rc;
         h->S_valid = true; h->last_conn_path = 1;
         return MP_OK;
@@ -445,7 +446,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     if (const char *env = getenv("MP_CONN_CULL")) h->conn_cull = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_GEMM")) h->use_gemm = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_GEMM_MIN_N")) { const int v = atoi(env); if (v >= 1) h->gemm_min_n = v; }
-    if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 2) h->conn_shape = v; }
+    if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 3) h->conn_shape = v; }
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
@@ -853,7 +854,9 @@ int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
     if ((rc = mp_set_params(h, par.data())) != MP_OK) return rc;
     if ((rc = mp_set_state(h, z.data(), y.data())) != MP_OK) return rc;
     h->sweep = 0; h->ndraws = 0;
-    if ((rc = mp_connectivity(h, nullptr)) != MP_OK) return rc;
+    // the sampler's resident S always comes from k_conn: its FP64 accumulation is what lets rank-1 removals cancel exactly
+    if ((rc = check_ready(h)) != MP_OK) return rc;
+    if ((rc = is64(h) ? refresh_S<double>(h, false) : refresh_S<float>(h, false)) != MP_OK) return rc;
     if (disperse) {
         // a dispersed start must be a possible state: an empty cell next year (y=0, z'=0) needs C < 1, i.e.
         // c < 1 / max(K_t S + Ksrc_t g); pull c below that bound (same rule as the CPU twin's spom_init_chain)

@@ -63,7 +63,7 @@ struct mp_engine {
     bool par_host_valid = false;               // ... still what the device holds (the sampler changes them on the device)
     int use_gemm = 1, gemm_min_n = 1024;       // tensor-core connectivity for chains sharing (alpha, b): MP_CONN_GEMM=0 disables, MP_CONN_GEMM_MIN_N
     int last_conn_path = 0;                    // 0: k_conn, 1: k_conn_gemm (mp_get_conn_path)
-    int conn_shape = 0;                        // CTA shape of k_conn: 0 choose, 1 = 128 threads x 2 targets, 2 = 64 x 2 (MP_CONN_SHAPE)
+    int conn_shape = 0;                        // CTA shape of k_conn: 0 choose, 1 = 128 threads x 2 targets, 2 = 64 x 2, 3 = 32 x 2 (MP_CONN_SHAPE)
     unsigned long long *d_work = nullptr;      // MP_CNT_* work counters (mp_get_work_counters)
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
     int *d_perm = nullptr;                     // scan (Morton) order of the patches: perm[slot] = patch

@@ -62,7 +62,8 @@ def oracle_values(name):
 
 @pytest.mark.parametrize("precision", [mb.FP64, mb.FP32], ids=["fp64", "fp32"])
 @pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "cfg4l"])
-def test_connectivity_and_loglik_at_baseline_shapes(name, precision):
+def test_connectivity_and_loglik_at_baseline_shapes(name, precision, monkeypatch):
+    monkeypatch.setenv("MP_CONN_GEMM", "0")      # one chain trivially "shares" (alpha, b): keep k_conn here (the tensor-core path: test_gpu_gemm.py)
     wl, spec, par, z, y, want, wparts, wS = oracle_values(name)
     assert np.isfinite(want)
     tol = RTOL[precision]
@@ -84,8 +85,9 @@ def test_connectivity_and_loglik_at_baseline_shapes(name, precision):
 
 
 @pytest.mark.parametrize("precision", [mb.FP64, mb.FP32], ids=["fp64", "fp32"])
-def test_connectivity_at_cfg5_on_sampled_targets(precision):
+def test_connectivity_at_cfg5_on_sampled_targets(precision, monkeypatch):
     """N=100,000 x T=30: S of 256 sampled target patches in three sampled years against the oracle."""
+    monkeypatch.setenv("MP_CONN_GEMM", "0")
     wl = synth.make_workload("cfg5")
     n, T = wl["n"], wl["T"]
     t = wl["truth"]

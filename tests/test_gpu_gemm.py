@@ -95,3 +95,30 @@ def test_gemm_at_cfg3_shape_vs_oracle_and_k_conn(monkeypatch):
         want, wparts, wS = O.loglik(m, oparams(par), z, ys[c], want_S=True)
         assert rel_err(S[c], wS, 1e-6 * wS.max()) <= TOL, rel_err(S[c], wS, 1e-6 * wS.max())
         assert abs(ll[c] - want) <= TOL * abs(want)
+
+
+def test_gemm_cfg5_sampled_targets_and_linearity():
+    """N=100,000 x T=30, one chain: 29 columns on the tensor cores against the oracle on 256 sampled targets; and the
+    contraction is linear in y to the FP32 accumulation error."""
+    wl = synth.make_workload("cfg5")
+    n, T = wl["n"], wl["T"]
+    t = wl["truth"]
+    par = pdict(e=t["e"], c=0.5 * t["c"], alpha=t["alpha"], b=t["b"])
+    rng = np.random.default_rng(3)
+    z = wl["z_true"].astype(np.uint8)
+    y = (z[:-1] & z[1:] & (rng.random((T - 1, n)) < 0.7)).astype(np.uint8)
+    ya = (y * (rng.random(y.shape) < 0.5)).astype(np.uint8)
+    spec = dict(geom=O.GEOM_COORDS, px=wl["px"], py=wl["py"], area=wl["area"], obs=wl["obs"])
+    m = make_model(spec)
+    with make_engine(spec, n_chains=1, precision=mb.FP32) as eng:
+        eng.set_params([par])
+        eng.set_state(z[None], y[None])
+        S = eng.connectivity()[0]
+        assert eng.conn_path() == "gemm"
+        eng.set_state(z[None], ya[None]); Sa = eng.connectivity()[0]
+        eng.set_state(z[None], (y - ya)[None]); Sb = eng.connectivity()[0]
+    targets = np.sort(rng.choice(n, 256, replace=False)).astype(np.int32)
+    for year in (0, T // 2, T - 2):
+        want = O.connectivity_targets(m, par["alpha"], par["b"], y[year], targets)
+        assert rel_err(S[year, targets], want, 1e-6 * want.max()) <= TOL
+    assert rel_err(Sa + Sb, S, 1e-6 * S.max()) <= TOL

@@ -608,10 +608,11 @@ def test_edge_shapes():
 
 
 # ------------------------------------------------------------------ full-size properties (BASELINE cfg3 shape)
-def test_full_size_properties_cfg3():
+def test_full_size_properties_cfg3(monkeypatch):
     """N=10,000 x T=20 (cfg3 shape), FP32 engine: connectivity is linear in y, the rank-1 log-odds
     equals the difference of two full evaluations, and after a sweep the incrementally updated S
     equals a from-scratch recomputation while the state stays feasible."""
+    monkeypatch.setenv("MP_CONN_GEMM", "0")      # properties of k_conn (FP64 accumulation); the tensor-core path: test_gpu_gemm.py
     rng = np.random.default_rng(12345)
     n, T, C = 10000, 20, 2
     spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.4, miss=0.05, areas=True)
