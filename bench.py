@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--ref-seconds", type=float, default=170.0, help="budget of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.* runs (weak figure, cfg5)")
+    ap.add_argument("--no-blocks", action="store_true", help="cfg5: scan every year as a whole (no block grid)")
+    ap.add_argument("--blocks-k", type=int, default=4, help="cfg5: colours per axis of the block grid")
+    ap.add_argument("--torch-collectives", action="store_true", help="cfg5 on several GPUs: round-1 exchange (torch.distributed all-reduce) instead of NCCL inside the library")
     ap.add_argument("--ess-sweeps", type=int, default=1000, help="extra sweeps after the timed regions for the ESS/s figure (0 = skip)")
     return ap.parse_args()
 
@@ -558,13 +561,23 @@ def run_cfg5(args, rank, local_rank, world, wl, steps, warmup):
     eng.set_observations(wl["obs"])
     eng.set_params([start_params(wl)] * C)
     eng.init_chains(mb.engine.sampler_config(**sampler_kwargs(wl)), disperse=False)
+    # block grid of the y scan: blocks of one colour are scanned concurrently (mp_set_scan_blocks); the halo comes from the
+    # start parameters and the smallest connectivity of the start state, with a margin for what the sampler does to them
+    grid = None
+    if not getattr(args, "no_blocks", False):
+        p0 = start_params(wl)
+        grid = eng.set_scan_blocks_auto(wl["px"], wl["py"], p0["alpha"], float(eng.get_connectivity().min()),
+                                        float(np.max(np.asarray(wl["area"]) ** p0["b"])), k=getattr(args, "blocks_k", 4))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sc = D.ShardedChain(eng, rank, world, dev) if world > 1 else None
+    sc = None
+    if world > 1:
+        sc = D.ShardedChain(eng, rank, world, dev) if getattr(args, "torch_collectives", False) else D.NativeShardedChain(eng)
     run = (lambda k: sc.sweep(k)) if sc else (lambda k: eng.sweep(k))
     run(W)
-    if sc:
+    if sc and hasattr(sc, "phase_s"):
         sc.phase_s = dict.fromkeys(sc.phase_s, 0.0)
     eng.get_timing(reset=True)
+    eng.work_counters(reset=True)
     times = []
     with ClockSampler(local_rank) as clk:
         for _ in range(K):
@@ -596,6 +609,8 @@ def run_cfg5(args, rank, local_rank, world, wl, steps, warmup):
                     config=dict(workload=f"cfg5: {wl['desc']}", n_patches=n, n_years=T, chains=C,
                                 parallelism=(sc.describe() if sc else "one engine on one GPU"),
                                 l2="flushed between timed steps (256 MiB write)", scan=eng.scan_geometry(),
+                                scan_blocks=(dict(nx=grid[0], ny=grid[1], colours=grid[2] ** 2, halo_m=round(grid[3], 1),
+                                                  block_tasks_per_sweep=eng.work_counters()["scan_blocks"] / K) if grid else None),
                                 timing="host clock between device synchronisations, max over ranks"),
                     clocks=clk.summary(), gpu_launches=int(sum(klaunch.values())),
                     ranks_hold_identical_draws=identical,
@@ -603,7 +618,8 @@ def run_cfg5(args, rank, local_rank, world, wl, steps, warmup):
                              note="state resident; the sharded loop has no per-step host buffers"))
         if sc:
             line["collective_bytes_per_sweep"] = int(sc.bytes_per_sweep())
-            line["phase_ms_per_sweep"] = {k: round(v / K * 1e3, 3) for k, v in sc.phase_s.items()}
+            if hasattr(sc, "phase_s"):
+                line["phase_ms_per_sweep"] = {k: round(v / K * 1e3, 3) for k, v in sc.phase_s.items()}
     eng.close()
     return line
 

@@ -98,6 +98,17 @@ int mp_set_source_units(mp_engine *h, const double *src_unit /* N or NULL => k+1
 /* Order in which the y scan visits the patches of a year (slot -> patch): the Morton order of planar
  * coordinates, index order for linear and dense landscapes (oracle: spom_scan_order). */
 int mp_get_scan_order(mp_engine *h, int32_t *order /* N */);
+/* Block grid of the y scan (planar coordinates only; no reference counterpart -- the reference has no sampler).
+ * The bounding box of the patches is cut into nx x ny cells and the cells are coloured k x k periodically.  The scan
+ * then visits the patches colour by colour, block by block, in Morton order inside a block (oracle: spom_scan_order
+ * with blk_nx, blk_ny, blk_k -- any fixed order is a valid Gibbs scan).  The FP32 engine scans the blocks of one colour
+ * CONCURRENTLY, one cluster per (chain, year, block), with the block's own patches and every patch within `halo` of
+ * its cell as targets: same-colour cells must lie farther apart than 2 halo ((k - 1) x cell width > 2 halo, else
+ * MP_ERR_ARG), so their target sets are disjoint.  Each sweep a (chain, year) is scanned by blocks only if the largest
+ * dispersal weight at the halo distance is below 2^-36 of the year's smallest S -- the commit rule the whole-year culled
+ * scan applies anyway -- and the year holds at least 64 occupied patches; otherwise that year falls back to the
+ * whole-year scan in the same order.  nx * ny <= 1 switches the grid off.  The FP64 engine only takes the order. */
+int mp_set_scan_blocks(mp_engine *h, int nx, int ny, int k, double halo);
 
 /* ---- data ---- */
 int mp_set_observations(mp_engine *h, const int8_t *obs /* T*N, -1/0/1 */);
@@ -138,6 +149,29 @@ int mp_synchronize(mp_engine *h);
  *     (exchange the owned rows of y and S afterwards), 3 e/p update + record.  mp_sweep == the four phases. */
 int mp_set_shard(mp_engine *h, int conn_lo, int conn_hi, int task_first, int task_stride);
 int mp_sweep_phase(mp_engine *h, int phase, int *flags_out);
+/* ---- several GPUs behind the C ABI (NCCL; replaces MPI_Init / the row split / the MPI_Send-MPI_Recv gather of
+ * main_MIDASPOM_MPI.c:344-372,483-505).  One process per GPU: rank 0 calls mp_comm_unique_id, ships the MP_COMM_ID_BYTES
+ * to the other ranks by whatever launcher it runs under, and every rank calls mp_comm_init.  One process driving several
+ * engines (one per device): mp_comm_init_all.  NCCL is loaded at the first of these calls (MP_ERR_UNSUPPORTED if absent).
+ *   mp_gather_draws   every rank's draws [first, first + count): out[rank][sweep][chain][MP_NDRAW], same on every rank
+ *                     (independent chains per rank, chain_offset = rank x n_chains)
+ *   mp_sweep_sharded  nsweeps iterations of ONE set of chains replicated on every rank: connectivity split by target
+ *                     patches (all-gather of the owned columns of S / S_prop), y scan split by (chain, year) tasks
+ *                     (broadcast of the owned rows of y and S), decisions replicated; equals mp_sweep on one engine bit
+ *                     for bit.  Everything is enqueued on the engine stream; no host synchronisation inside a sweep.
+ *                     In a single process call it for every engine of the communicator between mp_comm_group_begin /
+ *                     mp_comm_group_end is NOT needed: use mp_sweep_sharded_all instead. */
+#define MP_COMM_ID_BYTES 128
+int mp_comm_unique_id(void *id128);
+int mp_comm_init(mp_engine *h, int nranks, int rank, const void *id128);
+int mp_comm_init_all(mp_engine **engines, int n);
+int mp_comm_destroy(mp_engine *h);
+int mp_comm_rank(mp_engine *h);
+int mp_comm_size(mp_engine *h);
+const char *mp_comm_last_error(void);
+int mp_gather_draws(mp_engine *h, int first, int count, double *out /* nranks*count*C*MP_NDRAW */);
+int mp_sweep_sharded(mp_engine *h, int nsweeps);
+int mp_sweep_sharded_all(mp_engine **engines, int n, int nsweeps);
 int mp_num_draws(mp_engine *h);
 int mp_get_draws(mp_engine *h, int first, int count, double *out /* count*C*MP_NDRAW */);
 int mp_reset_draws(mp_engine *h);
@@ -186,16 +220,18 @@ int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset);
  *   MP_CNT_SCAN_DENSE    (candidate, target) pairs of the unculled scans (k_sweep_y_fast, k_sweep_y)
  *   MP_CNT_CONN_EXEC     (group of 32 targets, group of 32 sources) tiles of k_conn evaluated
  *   MP_CNT_CONN_TOTAL    the same, culled ones included
- *   MP_CNT_GEMM_TILES    128 x 128 x 64 tensor-core tiles issued by the fixed-(alpha, b) connectivity path */
+ *   MP_CNT_GEMM_TILES    128 x 128 x 64 tensor-core tiles issued by the fixed-(alpha, b) connectivity path
+ *   MP_CNT_SCAN_BLOCKS   block tasks of the y scan executed (mp_set_scan_blocks; 0: every year was scanned as a whole) */
 enum { MP_CNT_SCAN_TRIPS = 0, MP_CNT_SCAN_EXEC = 1, MP_CNT_SCAN_RETIRED = 2, MP_CNT_SCAN_COMMIT = 3, MP_CNT_SCAN_DENSE = 4,
-       MP_CNT_CONN_EXEC = 5, MP_CNT_CONN_TOTAL = 6, MP_CNT_GEMM_TILES = 7, MP_CNT_N = 8 };
+       MP_CNT_CONN_EXEC = 5, MP_CNT_CONN_TOTAL = 6, MP_CNT_GEMM_TILES = 7, MP_CNT_SCAN_BLOCKS = 8, MP_CNT_N = 9 };
 int mp_get_work_counters(mp_engine *h, uint64_t *out /* MP_CNT_N */, int reset);
 /* which kernel evaluated the connectivity last: 0 = k_conn (per-chain parameters, FP64 accumulation), 1 = the tensor-core
  * contraction k_conn_gemm (FP32 engines; taken by mp_connectivity / mp_loglik / mp_loglik_host when every chain holds the
  * same alpha and b as uploaded by mp_set_params, the matrix form c*M%*%pti of Rscript/simuls_traj.R:16,203,214) */
 int mp_get_conn_path(mp_engine *h);
 /* launch geometry of the last y scan: out4 = threads per (chain, year) task, CTAs per cluster, candidates evaluated per
- * trip (1 + speculative), 1 if the spatially culled kernel ran (0: k_sweep_y_fast; all 0: the generic FP64 k_sweep_y) */
+ * trip (1 + speculative), 1 if the spatially culled kernel ran, 2 if it ran block by block (mp_set_scan_blocks; the first
+ * three numbers then describe a block task) (0: k_sweep_y_fast; all 0: the generic FP64 k_sweep_y) */
 int mp_get_scan_geometry(mp_engine *h, int *out4);
 /* micro-benchmarks on the engine's device: out[0] MUFU.EX2 Gop/s, out[1] FP32 FMA GFMA/s,
  * out[2] FP64 add Gop/s, out[3] device copy GB/s (read+write) */

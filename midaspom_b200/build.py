@@ -13,8 +13,8 @@ LIB_DIR = PKG / "lib"
 OBJ_DIR = LIB_DIR / "obj"
 LIB = LIB_DIR / "libmidaspom_cuda.so"
 SOURCES = [CSRC / "mp_engine.cu", CSRC / "mp_sweep_fast_linear.cu", CSRC / "mp_sweep_fast_coords.cu",
-           CSRC / "mp_sweep_fast_dense.cu", CSRC / "mp_exact.cu", CSRC / "mp_conn_gemm.cu"]
-HEADERS = [CSRC / "mp_device.cuh", CSRC / "mp_kernels.cuh", CSRC / "mp_conn.cuh", CSRC / "mp_sweep_fast.cuh", CSRC / "mp_sweep_cull.cuh", CSRC / "mp_host.h",
+           CSRC / "mp_sweep_fast_dense.cu", CSRC / "mp_exact.cu", CSRC / "mp_conn_gemm.cu", CSRC / "mp_comm.cu"]
+HEADERS = [CSRC / "mp_device.cuh", CSRC / "mp_kernels.cuh", CSRC / "mp_conn.cuh", CSRC / "mp_sweep_fast.cuh", CSRC / "mp_sweep_cull.cuh", CSRC / "mp_host.h", CSRC / "mp_comm.h",
            PKG.parent / "include" / "libmidaspom_cuda.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + [str(o) for o, _ in results]
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + [str(o) for o, _ in results] + ["-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

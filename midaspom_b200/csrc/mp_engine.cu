@@ -3,7 +3,8 @@
 // No CPU fallback: without a usable sm_100 device every entry point returns MP_ERR_CUDA.
 #include "mp_host.h"
 #include "mp_kernels.cuh"
-#include "mp_sweep_fast.cuh"   // k_build_candidates, CandRec
+#include "mp_sweep_cull.cuh"   // k_build_candidates, CandRec, BlockTask, k_block_valid
+#include "mp_comm.h"
 
 using namespace mp;
 
@@ -126,17 +127,24 @@ template <typename R, int GEOM> static int launch_sweep_y_g(mp_engine *h)
 {
     Timed tm(h, MP_K_SWEEP_Y);
     constexpr int NT = sizeof(R) == 4 ? 1024 : 512;
-    const size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
+    size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
+    const size_t stride = (smem + 255) / 256 * 256;
+    const int ntask = h->cfg.n_chains * (h->cfg.n_years - 1);
+    // beyond one CTA's shared memory (about 13,600 patches in FP64) the per-task state lives in global scratch (slow, parity only)
+    const bool spill = smem > 227 * 1024;
+    if (spill && !h->d_scan_work) CK(cudaMalloc(&h->d_scan_work, stride * (size_t)ntask));
+    if (spill) smem = 16;
     auto kern = k_sweep_y<R, GEOM, NT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nthr = (int)std::min<size_t>(NT, ((nN(h) + 31) / 32) * 32);
-    kern<<<h->cfg.n_chains * (h->cfg.n_years - 1), nthr, smem, h->stream>>>(
+    kern<<<ntask, nthr, smem, h->stream>>>(
         sampler_dev(h), h->sweep, view<R>(h), h->d_par, (const R *)h->d_aw[0], h->have_era ? h->d_era : nullptr, h->d_z,
-        h->d_y, h->d_S[0], h->cfg.n_years, (const int *)h->d_perm, h->d_work);
+        h->d_y, h->d_S[0], h->cfg.n_years, (const int *)h->d_scan, h->d_work, spill ? h->d_scan_work : nullptr, stride);
     CK(cudaGetLastError());
     return MP_OK;
 }
 // ---- FP32 fast path (mp_sweep_fast.cuh; kernels live in mp_sweep_fast_{linear,coords,dense}.cu)
+extern "C" { static int build_block_tasks(mp_engine *h); }   // block tasks of the scan grid (mp_set_scan_blocks), defined with the C ABI below
 static int pick_cluster(int tasks, int sms, int max_cs)
 {
     // split each task over CS CTAs so that tasks*CS fills the SMs evenly; ties -> smaller CS
@@ -162,7 +170,7 @@ static int launch_sweep_y_fast(mp_engine *h)
         k_build_candidates<<<ntask, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
                                                            (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
                                                            h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS,
-                                                           h->task_first, h->task_stride, h->d_perm);
+                                                           h->task_first, h->task_stride, h->d_scan, h->d_minv);
         CK(cudaGetLastError());
         k_order_tasks<<<1, 1024, 0, h->stream>>>(h->d_cand_count, ntask, h->task_first, h->task_stride, h->d_task_order);
         CK(cudaGetLastError());
@@ -184,10 +192,34 @@ static int launch_sweep_y_fast(mp_engine *h)
         while (cs < 8 && ept * (size_t)(tpt / cs) * 16 + 2048 > 227 * 1024) cs *= 2;
     }
     // exact spatial culling of the evaluation (mp_sweep_cull.cuh) where positions exist and the landscape is large
-    const bool culled = h->fast_cull && h->geom != MP_GEOM_DENSE && (tpt == 512 || tpt >= 2048);
+    const bool culled = h->fast_cull && h->geom != MP_GEOM_DENSE && tpt >= 512;
     h->last_scan[0] = tpt; h->last_scan[1] = cs; h->last_scan[2] = culled ? (tpt > 1024 ? 4 : 2) : 1; h->last_scan[3] = culled;
+    if (culled && h->blk_active) {
+        // block grid: decide per task whether its halo suffices this sweep, scan those tasks colour by colour (the blocks of
+        // one colour concurrently), then the remaining tasks as whole years (clusters of the other kind return at once)
+        int rc;
+        if (h->blk_tasks_dirty && (rc = build_block_tasks(h)) != MP_OK) return rc;
+        k_block_valid<<<ntask_own, 256, 0, h->stream>>>(h->d_S[0], h->d_par, h->d_cand_count, n, ntrans, h->task_first, h->task_stride,
+                                                        h->blk_halo, std::log2(h->area_max), std::log2(h->area_min), h->d_blockmode);
+        CK(cudaGetLastError());
+        // threads per block task: the smallest of 512 ... 8192 that keeps 31 slots per thread; cluster as wide as the shared memory asks
+        int btpt = h->blk_tpt ? h->blk_tpt : 512;
+        while ((h->blk_nl_max + btpt - 1) / btpt > 31 && btpt < 8192) btpt *= 2;
+        int bcs = btpt > 1024 ? 8 : (h->blk_cs ? h->blk_cs : 4);
+        if (btpt <= 1024) {
+            const size_t ept = (size_t)(h->blk_nl_max + btpt - 1) / btpt;
+            while (bcs < 8 && ept * (size_t)(btpt / bcs) * 16 + 2048 > 227 * 1024) bcs *= 2;
+        }
+        h->last_scan[0] = btpt; h->last_scan[1] = bcs; h->last_scan[2] = btpt > 1024 ? 4 : 2; h->last_scan[3] = 2;
+        for (size_t col = 0; col < h->colour_n.size(); col++) {
+            if (h->colour_n[col] == 0) continue;
+            const void *bt = (const char *)h->d_btasks + (size_t)h->colour_off[col] * sizeof(mp::BlockTask);
+            if ((rc = mp_launch_sweep_cull_coords(h, bcs, btpt, h->blk_nl_max, h->colour_n[col], bt)) != MP_OK) return rc;
+        }
+    }
     if (culled)
-        return h->geom == MP_GEOM_LINEAR ? mp_launch_sweep_cull_linear(h, cs, tpt) : mp_launch_sweep_cull_coords(h, cs, tpt);
+        return h->geom == MP_GEOM_LINEAR ? mp_launch_sweep_cull_linear(h, cs, tpt, n, ntask_own, nullptr)
+                                         : mp_launch_sweep_cull_coords(h, cs, tpt, n, ntask_own, nullptr);
     switch (h->geom) {
     case MP_GEOM_LINEAR: return mp_launch_sweep_fast_linear(h, cs, tpt);
     case MP_GEOM_COORDS: return mp_launch_sweep_fast_coords(h, cs, tpt);
@@ -198,8 +230,6 @@ template <typename R> static int launch_sweep_y(mp_engine *h)
 {
     if (fast_sweep_ok(h)) return launch_sweep_y_fast(h);
     REQUIRE(h->task_first == 0 && h->task_stride == 1, MP_ERR_UNSUPPORTED, "year sharding needs the FP32 fast sweep");
-    const size_t smem = nN(h) * (sizeof(double) + sizeof(R) + 1) + 16;
-    REQUIRE(smem <= 227 * 1024, MP_ERR_UNSUPPORTED, "n_patches too large for the shared-memory resident y sweep");
     switch (h->geom) {
     case MP_GEOM_LINEAR: return launch_sweep_y_g<R, MP_GEOM_LINEAR>(h);
     case MP_GEOM_COORDS: return launch_sweep_y_g<R, MP_GEOM_COORDS>(h);
@@ -407,11 +437,12 @@ int mp_destroy(mp_engine *h)
     if (!h) return MP_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) mp_comm_destroy(h);
     drain_spans(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_srec, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_tile_box, h->d_mlow, h->d_work, h->d_gemm };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_scan, h->d_minv, h->d_tile_box, h->d_mlow, h->d_work, h->d_gemm, h->d_tlist, h->d_btasks, h->d_blockmode, h->d_scan_work, h->d_comm_send, h->d_comm_recv };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -450,6 +481,8 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
+    if (const char *env = getenv("MP_BLK_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->blk_tpt = v; }
+    if (const char *env = getenv("MP_BLK_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) h->blk_cs = v; }
     h->sm_count = prop.multiProcessorCount;
     auto fail = [&](const char *what, cudaError_t ce) {
         g_create_error = std::string("mp_create: ") + what + ": " + cudaGetErrorString(ce);
@@ -477,7 +510,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
-        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_work, MP_CNT_N * sizeof(unsigned long long) },
+        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_scan, N * sizeof(int) }, { (void **)&h->d_minv, N * sizeof(int) }, { (void **)&h->d_work, MP_CNT_N * sizeof(unsigned long long) },
         { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) }, { (void **)&h->d_mlow, C * ((N + 31) / 32) * sizeof(float) },
     };
     for (auto &r : reqs) {
@@ -520,28 +553,54 @@ static int set_area(mp_engine *h, const double *area)
     }
     return MP_OK;
 }
-// Morton (Z-order) permutation of the patches: perm[slot] = patch.  Spatially adjacent
-// patches get adjacent slots, which is what makes the warp-level culling of k_sweep_y_cull effective.
+// cell of a coordinate in a grid of ncell cells over [lo, hi] -- the same arithmetic as the oracle's scan_cell
+static inline int scan_cell(double v, double lo, double hi, int ncell)
+{
+    const double w = (hi - lo) / ncell;
+    if (!(w > 0.0)) return 0;
+    int c = (int)((v - lo) / w);
+    if (c < 0) c = 0;
+    if (c > ncell - 1) c = ncell - 1;
+    return c;
+}
+// Two orders of the patches.  LAYOUT order perm[slot] = patch: the Morton (Z-curve) order of planar coordinates, index order
+// otherwise -- spatially adjacent patches get adjacent slots, which is what makes the warp-level culling of k_sweep_y_cull
+// and k_conn effective.  VISITING order of the y scan scan[pos] = patch: the same without a scan grid; with one
+// (mp_set_scan_blocks) colour by colour, block by block, Morton order inside a block (oracle: spom_scan_order).
 static int set_patch_order(mp_engine *h, const double *x, const double *y, double spacing = 0.0, double cx = 0.0, double cy = 0.0)
 {   // (cx, cy): origin of the coordinates as stored on the device (FP32 engines centre them)
     const size_t N = nN(h);
-    std::vector<int> perm(N);
-    for (size_t i = 0; i < N; i++) perm[i] = (int)i;
+    std::vector<int> perm(N), scan(N), minv(N);
+    for (size_t i = 0; i < N; i++) perm[i] = scan[i] = (int)i;
+    h->morton.assign(N, 0u); h->blk_of.assign(N, 0);
     if (x && y) {
+        if (x != h->hx.data()) { h->hx.assign(x, x + N); h->hy.assign(y, y + N); }
+        h->cx = cx; h->cy = cy;
         double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
         for (size_t i = 1; i < N; i++) { x0 = std::min(x0, x[i]); x1 = std::max(x1, x[i]); y0 = std::min(y0, y[i]); y1 = std::max(y1, y[i]); }
+        h->bb[0] = x0; h->bb[1] = x1; h->bb[2] = y0; h->bb[3] = y1;
         const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
         auto spread = [](uint32_t v) { v &= 0xffffu; v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu;
                                        v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u; return v; };
-        std::vector<uint32_t> code(N);
+        const int nbx = std::max(h->blk_nx, 1), nby = std::max(h->blk_ny, 1), bk = std::max(h->blk_k, 1);
+        std::vector<uint64_t> key(N);
         for (size_t i = 0; i < N; i++) {
             const uint32_t xi = (uint32_t)std::min(65535.0, (x[i] - x0) / span * 65535.0), yi = (uint32_t)std::min(65535.0, (y[i] - y0) / span * 65535.0);
-            code[i] = spread(xi) | (spread(yi) << 1);
+            h->morton[i] = spread(xi) | (spread(yi) << 1);
+            const int bx = scan_cell(x[i], x0, x1, nbx), by = scan_cell(y[i], y0, y1, nby);
+            h->blk_of[i] = by * nbx + bx;
+            const uint32_t group = (uint32_t)(((bx % bk) + bk * (by % bk)) * (nbx * nby) + by * nbx + bx);   // (colour, block)
+            key[i] = ((uint64_t)group << 32) | h->morton[i];
         }
-        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return code[a] < code[b]; });
-    }
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return h->morton[a] < h->morton[b]; });
+        std::stable_sort(scan.begin(), scan.end(), [&](int a, int b) { return key[a] < key[b]; });
+    } else { h->hx.clear(); h->hy.clear(); }
+    for (size_t s = 0; s < N; s++) minv[perm[s]] = (int)s;
+    h->scan_host = scan;
     CK(cudaMemcpy(h->d_perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
-    // bounding boxes of the groups of 32 consecutive slots (culled k_conn), in the FP32 coordinates the kernels use
+    CK(cudaMemcpy(h->d_scan, scan.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_minv, minv.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    // bounding boxes of the groups of 32 consecutive layout slots (culled k_conn), in the FP32 coordinates the kernels use
     const size_t ntile = (N + 31) / 32;
     std::vector<float4> box(ntile);
     h->have_boxes = (x && y) || spacing > 0.0;
@@ -557,14 +616,100 @@ static int set_patch_order(mp_engine *h, const double *x, const double *y, doubl
     CK(cudaMemcpy(h->d_tile_box, box.data(), ntile * sizeof(float4), cudaMemcpyHostToDevice));
     return MP_OK;
 }
+// Block lists of the scan grid: per block its run of scan-order slots and its target list -- own patches in scan order,
+// then every other patch within the halo of the block's cell, in Morton order (32 consecutive list entries stay compact).
+static int build_scan_blocks(mp_engine *h)
+{
+    const size_t N = nN(h);
+    const int nbx = h->blk_nx, nby = h->blk_ny, nb = nbx * nby;
+    h->blk_slot_lo.assign(nb, 0); h->blk_slot_hi.assign(nb, 0); h->blk_tl_off.assign(nb, 0); h->blk_tl_n.assign(nb, 0);
+    std::vector<int> seen(nb, 0);
+    for (size_t s = 0; s < N; s++) {                      // own positions: contiguous runs of the (colour, block, Morton) visiting order
+        const int b = h->blk_of[h->scan_host[s]];
+        if (!seen[b]) { seen[b] = 1; h->blk_slot_lo[b] = (int)s; }
+        h->blk_slot_hi[b] = (int)s + 1;
+    }
+    const double x0 = h->bb[0], x1 = h->bb[1], y0 = h->bb[2], y1 = h->bb[3];
+    const double wx = (x1 - x0) / nbx, wy = (y1 - y0) / nby, halo2 = h->blk_halo * h->blk_halo;
+    std::vector<int> by_morton(N);
+    for (size_t i = 0; i < N; i++) by_morton[i] = (int)i;
+    std::stable_sort(by_morton.begin(), by_morton.end(), [&](int a, int b) { return h->morton[a] < h->morton[b]; });
+    std::vector<int> tlist;
+    h->blk_nl_max = 0;
+    for (int b = 0; b < nb; b++) {
+        h->blk_tl_off[b] = (int)tlist.size();
+        if (!seen[b]) continue;
+        for (int s = h->blk_slot_lo[b]; s < h->blk_slot_hi[b]; s++) tlist.push_back(h->scan_host[s]);
+        const int bx = b % nbx, by = b / nbx;
+        const double rx0 = x0 + bx * wx, rx1 = x0 + (bx + 1) * wx, ry0 = y0 + by * wy, ry1 = y0 + (by + 1) * wy;
+        for (size_t i = 0; i < N; i++) {
+            const int q = by_morton[i];
+            if (h->blk_of[q] == b) continue;
+            const double dx = std::max(std::max(rx0 - h->hx[q], h->hx[q] - rx1), 0.0), dy = std::max(std::max(ry0 - h->hy[q], h->hy[q] - ry1), 0.0);
+            if (dx * dx + dy * dy <= halo2) tlist.push_back(q);
+        }
+        h->blk_tl_n[b] = (int)tlist.size() - h->blk_tl_off[b];
+        h->blk_nl_max = std::max(h->blk_nl_max, h->blk_tl_n[b]);
+        while (tlist.size() % 4) tlist.push_back(0);      // 16-byte aligned lists
+    }
+    if (h->d_tlist) { CK(cudaFree(h->d_tlist)); h->d_tlist = nullptr; }
+    CK(cudaMalloc(&h->d_tlist, std::max<size_t>(tlist.size(), 4) * sizeof(int)));
+    CK(cudaMemcpy(h->d_tlist, tlist.data(), tlist.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->blk_tasks_dirty = true;
+    return MP_OK;
+}
+// Block tasks of the (chain, year) tasks this engine scans, grouped by colour (one launch per colour)
+static int build_block_tasks(mp_engine *h)
+{
+    const int nbx = h->blk_nx, nby = h->blk_ny, bk = h->blk_k, nb = nbx * nby, ncol = bk * bk;
+    const int ntask_all = h->cfg.n_chains * (h->cfg.n_years - 1);
+    std::vector<mp::BlockTask> bt;
+    h->colour_off.assign(ncol, 0); h->colour_n.assign(ncol, 0);
+    for (int col = 0; col < ncol; col++) {
+        h->colour_off[col] = (int)bt.size();
+        for (int b = 0; b < nb; b++) {
+            const int bx = b % nbx, by = b / nbx;
+            if ((bx % bk) + bk * (by % bk) != col || h->blk_slot_hi[b] <= h->blk_slot_lo[b]) continue;
+            for (int task = h->task_first; task < ntask_all; task += h->task_stride)
+                bt.push_back(mp::BlockTask{ task, h->blk_tl_off[b], h->blk_tl_n[b], h->blk_slot_lo[b], h->blk_slot_hi[b] });
+        }
+        h->colour_n[col] = (int)bt.size() - h->colour_off[col];
+    }
+    if (h->d_btasks) { CK(cudaFree(h->d_btasks)); h->d_btasks = nullptr; }
+    CK(cudaMalloc(&h->d_btasks, std::max<size_t>(bt.size(), 1) * sizeof(mp::BlockTask)));
+    CK(cudaMemcpy(h->d_btasks, bt.data(), bt.size() * sizeof(mp::BlockTask), cudaMemcpyHostToDevice));
+    if (!h->d_blockmode) { CK(cudaMalloc(&h->d_blockmode, (size_t)ntask_all * sizeof(int))); CK(cudaMemset(h->d_blockmode, 0, (size_t)ntask_all * sizeof(int))); }
+    h->blk_tasks_dirty = false;
+    return MP_OK;
+}
 int mp_get_scan_order(mp_engine *h, int32_t *order)
 {
     if (!h || !order) return MP_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
     REQUIRE(h->have_landscape, MP_ERR_STATE, "set the landscape first");
     if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
-    CK(cudaMemcpy(order, h->d_perm, nN(h) * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(order, h->d_scan, nN(h) * sizeof(int), cudaMemcpyDeviceToHost));
     return MP_OK;
+}
+int mp_set_scan_blocks(mp_engine *h, int nx, int ny, int k, double halo)
+{
+    if (!h) return MP_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    REQUIRE(h->have_landscape && h->geom == MP_GEOM_COORDS, MP_ERR_STATE, "mp_set_scan_blocks: set a landscape with coordinates first");
+    if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
+    const bool on = nx >= 1 && ny >= 1 && nx * ny > 1;
+    if (on) {
+        REQUIRE(k >= 2 && halo >= 0.0 && nx <= 1024 && ny <= 1024, MP_ERR_ARG, "mp_set_scan_blocks: need k >= 2, halo >= 0, at most 1024 cells per axis");
+        // same-colour cells are k cells apart along an axis with more than k cells: the gap (k - 1) cells must exceed 2 halo
+        const double wx = (h->bb[1] - h->bb[0]) / nx, wy = (h->bb[3] - h->bb[2]) / ny;
+        REQUIRE((nx <= k || (k - 1) * wx > 2.0 * halo) && (ny <= k || (k - 1) * wy > 2.0 * halo), MP_ERR_ARG,
+                "mp_set_scan_blocks: cells of one colour must lie farther apart than twice the halo ((k - 1) x cell width > 2 halo)");
+    }
+    h->blk_nx = on ? nx : 1; h->blk_ny = on ? ny : 1; h->blk_k = on ? k : 1; h->blk_halo = on ? halo : 0.0; h->blk_active = on;
+    std::vector<double> x = h->hx, y = h->hy;             // set_patch_order re-reads the caller's coordinates
+    int rc = set_patch_order(h, x.data(), y.data(), 0.0, h->cx, h->cy);
+    if (rc != MP_OK) return rc;
+    return on ? build_scan_blocks(h) : MP_OK;
 }
 int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
 {
@@ -573,6 +718,7 @@ int mp_set_landscape_linear(mp_engine *h, double spacing, const double *area)
     if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(spacing > 0.0, MP_ERR_ARG, "spacing must be positive");
     h->geom = MP_GEOM_LINEAR; h->spacing = spacing;
+    h->blk_nx = h->blk_ny = h->blk_k = 1; h->blk_halo = 0.0; h->blk_active = false;   // a new landscape starts without a scan grid
     int rc = set_patch_order(h, nullptr, nullptr, spacing);      // a line is already in spatial order
     if (rc != MP_OK) return rc;
     rc = set_area(h, area);
@@ -586,6 +732,7 @@ int mp_set_landscape_coords(mp_engine *h, const double *x, const double *y, cons
     if (quiesce(h) != MP_OK) return MP_ERR_CUDA;
     REQUIRE(x && y, MP_ERR_ARG, "null coordinates");
     h->geom = MP_GEOM_COORDS;
+    h->blk_nx = h->blk_ny = h->blk_k = 1; h->blk_halo = 0.0; h->blk_active = false;   // a new landscape starts without a scan grid
     int rc;
     // FP32 engines store positions relative to the centre of the bounding box: only differences enter the model, and
     // halving the largest magnitude halves the quantisation of a coordinate (2^-24 of it).  FP64 keeps the caller's values.
@@ -615,6 +762,7 @@ int mp_set_landscape_dense(mp_engine *h, const double *dist, const double *area)
     const size_t nn = nN(h) * nN(h);
     if (!h->d_dist) CK(cudaMalloc(&h->d_dist, nn * rsz(h)));
     h->geom = MP_GEOM_DENSE;
+    h->blk_nx = h->blk_ny = h->blk_k = 1; h->blk_halo = 0.0; h->blk_active = false;   // a new landscape starts without a scan grid
     int rc;
     if ((rc = upload_real(h, h->d_dist, dist, nn)) != MP_OK) return rc;
     if ((rc = set_patch_order(h, nullptr, nullptr)) != MP_OK) return rc;
@@ -913,6 +1061,7 @@ int mp_set_shard(mp_engine *h, int conn_lo, int conn_hi, int task_first, int tas
     REQUIRE(conn_hi < 0 || (conn_lo % 256 == 0 && (conn_hi % 256 == 0 || conn_hi == h->cfg.n_patches)), MP_ERR_ARG,
             "mp_set_shard: conn_lo and conn_hi must be multiples of 256 (conn_hi may also be n_patches)");
     h->conn_lo = conn_hi < 0 ? 0 : conn_lo; h->conn_hi = conn_hi; h->task_first = task_first; h->task_stride = task_stride;
+    h->blk_tasks_dirty = true;
     return MP_OK;
 }
 int mp_sweep_phase(mp_engine *h, int phase, int *flags_out)
@@ -932,6 +1081,91 @@ int mp_sweep_phase(mp_engine *h, int phase, int *flags_out)
     default: h->err = "mp_sweep_phase: unknown phase"; return MP_ERR_ARG;
     }
 }
+// ---- one set of chains over the ranks of a communicator (mp_comm.cu): the phases of a sweep with NCCL between them
+// owned connectivity columns (layout slots [lo, lo + per) of every row of S) <-> a dense [row][per] buffer
+static __global__ void k_pack_cols(const double *__restrict__ S, const int *__restrict__ perm, int n, int lo, int per, double *__restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (s < per) out[(size_t)row * per + s] = lo + s < n ? S[(size_t)row * n + perm[lo + s]] : 0.0;
+}
+static __global__ void k_unpack_cols(double *__restrict__ S, const int *__restrict__ perm, int n, int per, int rows, const double *__restrict__ in)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y, r = blockIdx.z;
+    if (s < per && r * per + s < n) S[(size_t)row * n + perm[r * per + s]] = in[((size_t)r * rows + row) * per + s];
+}
+enum { SH_CONN = 0, SH_GATHER = 1, SH_SCAN = 2, SH_ROWS = 3, SH_FINISH = 4 };
+static int sharded_stage(mp_engine *h, int stage)
+{
+    CK(cudaSetDevice(h->cfg.device));
+    const int n = h->cfg.n_patches, rows = h->cfg.n_chains * (h->cfg.n_years - 1), per = h->comm_per, W = h->comm_size;
+    const dim3 pgrid((per + 255) / 256, rows), ugrid((per + 255) / 256, rows, W);
+    int rc;
+    switch (stage) {
+    case SH_CONN:
+        if ((rc = phase_propose_conn<float>(h, &h->shard_flags)) != MP_OK) return rc;
+        for (int set = 0; set < 2; set++)
+            if ((h->shard_flags >> set) & 1) {
+                k_pack_cols<<<pgrid, 256, 0, h->stream>>>(h->d_S[set], h->d_perm, n, h->conn_lo, per, h->d_comm_send + (size_t)set * rows * per);
+                CK(cudaGetLastError());
+            }
+        return MP_OK;
+    case SH_GATHER:
+        for (int set = 0; set < 2; set++)
+            if ((h->shard_flags >> set) & 1)
+                if ((rc = mp_comm_allgather(h, h->d_comm_send + (size_t)set * rows * per, h->d_comm_recv + (size_t)set * W * rows * per,
+                                            (size_t)rows * per * 8)) != MP_OK) return rc;
+        return MP_OK;
+    case SH_SCAN:
+        for (int set = 0; set < 2; set++)
+            if ((h->shard_flags >> set) & 1) {
+                k_unpack_cols<<<ugrid, 256, 0, h->stream>>>(h->d_S[set], h->d_perm, n, per, rows, h->d_comm_recv + (size_t)set * W * rows * per);
+                CK(cudaGetLastError());
+            }
+        if ((rc = phase_decide_z<float>(h)) != MP_OK) return rc;
+        return phase_sweep_y<float>(h);
+    case SH_ROWS:   // the owner of (chain, year) task r is rank r mod W: its rows of y and S go to everybody
+        for (int row = 0; row < rows; row++) {
+            if ((rc = mp_comm_broadcast(h, h->d_S[0] + (size_t)row * n, (size_t)n * 8, row % W)) != MP_OK) return rc;
+            if ((rc = mp_comm_broadcast(h, h->d_y + (size_t)row * n, (size_t)n, row % W)) != MP_OK) return rc;
+        }
+        return MP_OK;
+    default:
+        return phase_finish<float>(h);
+    }
+}
+static int sharded_prepare(mp_engine *h)
+{
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = check_ready(h);
+    if (rc != MP_OK) return rc;
+    REQUIRE(h->comm, MP_ERR_STATE, "mp_sweep_sharded: no communicator (mp_comm_init / mp_comm_init_all)");
+    REQUIRE(h->have_sc && h->have_obs, MP_ERR_STATE, "sampler not configured (mp_init_chains / mp_set_sampler)");
+    REQUIRE(!is64(h), MP_ERR_UNSUPPORTED, "sharded sweeps need the FP32 engine");
+    const int n = h->cfg.n_patches, per = h->comm_per, W = h->comm_size, r = h->comm_rank;
+    const size_t rows = nC(h) * (nT(h) - 1);
+    if ((rc = mp_set_shard(h, std::min(n, r * per), std::min(n, (r + 1) * per), r, W)) != MP_OK) return rc;
+    if (!h->d_comm_send) {
+        CK(cudaMalloc(&h->d_comm_send, 2 * rows * per * 8));
+        CK(cudaMalloc(&h->d_comm_recv, 2 * rows * per * 8 * (size_t)W));
+    }
+    h->par_host_valid = false;
+    return MP_OK;
+}
+int mp_sweep_sharded_all(mp_engine **hs, int n, int nsweeps)
+{
+    if (!hs || n < 1 || !hs[0]) return MP_ERR_ARG;
+    int rc;
+    for (int i = 0; i < n; i++) { if (!hs[i]) return MP_ERR_ARG; if ((rc = sharded_prepare(hs[i])) != MP_OK) return rc; }
+    for (int s = 0; s < nsweeps; s++)
+        for (int stage = SH_CONN; stage <= SH_FINISH; stage++) {
+            const bool coll = stage == SH_GATHER || stage == SH_ROWS;   // the collectives of all local engines form one NCCL group
+            if (coll && (rc = mp_comm_group_start(hs[0])) != MP_OK) return rc;
+            for (int i = 0; i < n; i++) if ((rc = sharded_stage(hs[i], stage)) != MP_OK) return rc;
+            if (coll && (rc = mp_comm_group_end(hs[0])) != MP_OK) return rc;
+        }
+    return MP_OK;
+}
+int mp_sweep_sharded(mp_engine *h, int nsweeps) { return mp_sweep_sharded_all(&h, 1, nsweeps); }
 int mp_synchronize(mp_engine *h)
 {
     if (!h) return MP_ERR_ARG;

@@ -66,11 +66,34 @@ struct mp_engine {
     int conn_shape = 0;                        // CTA shape of k_conn: 0 choose, 1 = 128 threads x 2 targets, 2 = 64 x 2, 3 = 32 x 2 (MP_CONN_SHAPE)
     unsigned long long *d_work = nullptr;      // MP_CNT_* work counters (mp_get_work_counters)
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
-    int *d_perm = nullptr;                     // scan (Morton) order of the patches: perm[slot] = patch
+    int *d_perm = nullptr;                     // layout (Morton) order of the patches: perm[slot] = patch
+    int *d_scan = nullptr, *d_minv = nullptr;  // visiting order of the y scan (position -> patch; = perm without a scan grid); patch -> layout slot
     int fast_cull = 1;               // exact spatial culling in the fast sweep (MP_FAST_CULL=0 disables)
     int fast_cs = 0;                 // cluster size of the fast sweep (0 = choose); MP_FAST_CS overrides
     int fast_tpt = 0;                // threads per task of the fast sweep (0 = choose from N); MP_FAST_TPT overrides
+    // block grid of the y scan (landscapes with coordinates; mp_set_scan_blocks): blk_nx x blk_ny cells, blk_k x blk_k colours
+    int blk_nx = 1, blk_ny = 1, blk_k = 1;
+    double blk_halo = 0.0;            // targets of a block: its own patches and every patch within this distance of its cell
+    bool blk_active = false;          // more than one block: the scan runs colour by colour
+    bool blk_tasks_dirty = true;      // the per-colour task lists depend on the chains and on the year sharding
+    std::vector<double> hx, hy;       // the caller's coordinates (scan order and block lists are derived from them)
+    double cx = 0.0, cy = 0.0, bb[4] = { 0, 0, 0, 0 };   // origin of the device coordinates; bounding box x0, x1, y0, y1 of the caller's
+    std::vector<uint32_t> morton;     // Morton code of every patch
+    std::vector<int> blk_of, scan_host;   // block of every patch; visiting order of the scan (position -> patch)
+    int blk_tpt = 0, blk_cs = 0;      // threads per block task / cluster size (0 = choose); MP_BLK_TPT, MP_BLK_CS override
+    std::vector<int> blk_slot_lo, blk_slot_hi, blk_tl_off, blk_tl_n;   // per block: own scan-order slots, target list
+    std::vector<int> colour_off, colour_n;     // per colour: first block task and count in d_btasks
+    int blk_nl_max = 0;               // largest target list
+    int *d_tlist = nullptr;           // concatenated target lists (patch numbers)
+    void *d_btasks = nullptr;         // mp::BlockTask of every (owned task, block), grouped by colour
+    unsigned char *d_scan_work = nullptr;   // global scratch of the generic y scan on landscapes beyond one CTA's shared memory
+    int *d_blockmode = nullptr;       // [chain] 1: this sweep's scan of the chain runs by blocks (k_block_valid)
     int last_scan[4] = { 0, 0, 0, 0 };   // geometry of the last y scan launched: threads per task, cluster size, candidates per trip, culled
+    // communicator (mp_comm.cu): NCCL behind the C ABI
+    void *comm = nullptr;             // ncclComm_t
+    int comm_size = 1, comm_rank = 0, comm_per = 0;   // comm_per: scan-order slots per rank of the sharded connectivity
+    double *d_comm_send = nullptr, *d_comm_recv = nullptr;   // packed connectivity columns of the sharded sweep
+    int shard_flags = 0;              // what phase 0 of the current sharded sweep computed (bit 0: S, bit 1: S_prop)
     // timing
     bool timing = false;
     struct Span { cudaEvent_t a, b; int cat; };
@@ -145,7 +168,8 @@ template <typename R> inline mp::Landscape<R> view(const mp_engine *h)
 int mp_launch_sweep_fast_linear(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_fast_coords(mp_engine *h, int cs, int tpt);
 int mp_launch_sweep_fast_dense(mp_engine *h, int cs, int tpt);
-int mp_launch_sweep_cull_linear(mp_engine *h, int cs, int tpt);
-int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt);
+// culled scan: nclusters whole (chain, year) tasks (btasks == nullptr) or block tasks (mp::BlockTask array on the device)
+int mp_launch_sweep_cull_linear(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks);
+int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks);
 // tensor-core connectivity of every chain with one (alpha, b) (mp_conn_gemm.cu)
 int mp_launch_conn_gemm(mp_engine *h, double alpha);

@@ -450,12 +450,16 @@ __global__ void __launch_bounds__(NT, 1)
 k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
           const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S, int T,
           const int *__restrict__ order /* visiting order of the scan: slot -> patch (oracle: spom_scan_order) */,
-          unsigned long long *__restrict__ stats)
+          unsigned long long *__restrict__ stats,
+          unsigned char *__restrict__ work /* landscapes beyond one CTA's shared memory: per-task scratch in global memory (L2 resident), else nullptr */,
+          size_t work_stride)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, nthr = blockDim.x;
     const int c = blockIdx.x / ntrans, t = blockIdx.x - c * ntrans;
-    double *sS = reinterpret_cast<double *>(smem_raw);
+    // every thread reads and writes only its own targets q = tid, tid + nthr, ...; the candidate's own cell is read by all
+    // threads but written once, before the block barrier that precedes its visit -- so global scratch needs no more fences
+    double *sS = reinterpret_cast<double *>(work ? work + (size_t)blockIdx.x * work_stride : smem_raw);
     R *sL = reinterpret_cast<R *>(sS + n);
     uint8_t *sF = reinterpret_cast<uint8_t *>(sL + n);        // bit0 y, bit1 z_t, bit2 z_t+1
     __shared__ double warp_part[2][32];

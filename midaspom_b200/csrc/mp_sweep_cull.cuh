@@ -35,12 +35,23 @@
 
 namespace mp {
 
+// One unit of work of a block launch: the candidates of one block of the scan grid in one (chain, year) task, with the
+// block's own patches and every patch within the halo around it as targets (mp_set_scan_blocks).  Blocks of one colour
+// lie farther apart than twice the halo, so their target sets are disjoint and their scans run concurrently.
+struct BlockTask { int task, tl_off, nl, slot_lo, slot_hi; };
+
+// CTAs of NT threads that should share an SM (registers: about 96 per thread)
+__host__ __device__ constexpr int cull_min_blocks(int nt) { return nt <= 32 ? 17 : nt <= 64 ? 9 : nt <= 128 ? 5 : nt <= 256 ? 2 : 1; }
+
 template <int GEOM, int CS, int TPT>
-__global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : CS == 16 ? 17 : CS == 8 ? 9 : CS == 4 ? 5 : CS == 2 ? 2 : 1)
+__global__ void __launch_bounds__(TPT / CS, TPT > 1024 ? 1 : cull_min_blocks(TPT / CS))
 k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_params *__restrict__ par,
                const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S,
-               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept, const int *__restrict__ order,
-               unsigned long long *__restrict__ stats /* MP_CNT_SCAN_* work counters of the engine (mp_get_work_counters) */)
+               const CandRec *__restrict__ rec, const int *__restrict__ count, int T, int ept_max, const int *__restrict__ order,
+               unsigned long long *__restrict__ stats /* MP_CNT_SCAN_* work counters of the engine (mp_get_work_counters) */,
+               const BlockTask *__restrict__ btasks /* block launch: one entry per cluster (order is unused); nullptr: whole (chain, year) tasks */,
+               const int *__restrict__ tlist /* block launch: target lists (patch numbers) */,
+               const int *__restrict__ blockmode /* per (chain, year) task: 1 = scanned by the block launches, 0 = by the whole-task launch (nullptr: no block grid) */)
 {
     static_assert(GEOM != MP_GEOM_DENSE, "culling needs positions");
     constexpr int NT = TPT / CS, NW = NT / 32, SP = TPT > 1024 ? MP_CULL_SPEC_LARGE : MP_CULL_SPEC;
@@ -53,10 +64,18 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     __shared__ __align__(8) unsigned long long mbar[2][2];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
-    const int task = order[blockIdx.x / CS];                         // longest task first (k_order_tasks)
+    // what this cluster scans: a whole (chain, year) task (targets = all patches in scan order) or one block of it
+    const BlockTask bt = btasks ? btasks[blockIdx.x / CS] : BlockTask{ order[blockIdx.x / CS] /* longest task first (k_order_tasks) */, 0, n, 0, n };
+    const int task = bt.task;
     const int c = task / ntrans, t = task - c * ntrans;
+    // a (chain, year) task is scanned either by the block launches or by the whole-task launch, decided per sweep
+    // (k_block_valid); the whole cluster takes the same branch, before any cluster-wide synchronisation
+    if (blockmode && (blockmode[task] != 0) != (btasks != nullptr)) return;
+    const int nl = bt.nl;                                            // targets of this cluster
+    const int *tl = btasks ? tlist + bt.tl_off : perm;               // local slot -> patch
+    const int ept = (nl + TPT - 1) / TPT;                            // slots per thread (<= ept_max, which sizes the shared memory)
     float4 *sT = reinterpret_cast<float4 *>(smem_raw);               // {S_hi, S_lo, x, y} (COORDS) or {S_hi, S_lo, patch, -} (LINEAR)
-    float4 *ring = sT + ept * NT;                                    // 2 chunks of RC candidate records (two float4 each)
+    float4 *ring = sT + ept_max * NT;                                // 2 chunks of RC candidate records (two float4 each)
 
     const Trans<float> tr = make_trans<float>(par[c], era ? era[t] : 0);
     const float cK = tr.c * tr.Kt;
@@ -77,7 +96,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     float Gx = 0.f, Gy = 0.f, Gr = 3.0e38f, Gw = 0.f;
     for (int j = 0; j < ept; j++) {
         const int s = g + j * TPT;
-        const int q = s < n ? perm[s] : -1;
+        const int q = s < nl ? tl[s] : -1;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q >= 0) {
             if (GEOM == MP_GEOM_COORDS) { v.z = ls.px[q]; v.w = ls.py[q]; }
@@ -117,9 +136,24 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     const uint32_t red_remote = CS > 1 ? map_to_rank(smem_u32(&red[0][0][0]), (uint32_t)(lane < CS ? lane : 0)) : 0u;
     const uint32_t bar_remote = CS > 1 ? map_to_rank(smem_u32(&mbar[0][0]), (uint32_t)(lane < CS ? lane : 0)) : 0u;
     const uint32_t bar_local = smem_u32(&mbar[0][0]);
-    const int ncand = count[2 * task];
-    int nocc = count[2 * task + 1];
+    // candidates: the task's list is in visiting order; a block owns the contiguous run whose positions lie in [slot_lo, slot_hi)
     const CandRec *recs = rec + (size_t)task * n;
+    int ncand = count[2 * task];
+    int nocc = count[2 * task + 1];
+    if (btasks) {
+        auto first_at_least = [&](int slot) {                        // first candidate whose scan-order slot is >= slot
+            int lo = 0, hi = ncand;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)recs[mid].pad[1] < slot) lo = mid + 1; else hi = mid; }
+            return lo;
+        };
+        const int i0 = first_at_least(bt.slot_lo), i1 = first_at_least(bt.slot_hi);
+        recs += i0; ncand = i1 - i0;
+        nocc = 1 << 30;   // other blocks change the year's occupancy count concurrently; "the last occupied patch left" cannot arise (k_block_valid)
+    }
+    // slot of a candidate among the targets: whole tasks lay the targets out in Morton order (record field pad[0]); a block's
+    // list starts with its own patches in visiting order (pad[1] - slot_lo)
+    const int slot_lo = bt.slot_lo;
+    const bool blk = btasks != nullptr;
     uint32_t uses[2] = { 0u, 0u };
     // work counters of this warp (warp-uniform values, added to the engine's totals once at the end): trips, (candidate,
     // 32-target group) evaluations executed, the part of them that belongs to retired candidates, groups committed
@@ -220,7 +254,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
         const float4 a = ring[(i & (2 * RC - 1)) * 2], b = ring[(i & (2 * RC - 1)) * 2 + 1];
         Cand cd;
         cd.k = (int)(__float_as_uint(a.x) & 0x7fffffffu); cd.cur = __float_as_uint(a.x) >> 31;
-        cd.kx = a.y; cd.ky = a.z; cd.lawk = a.w; cd.thr = b.x; cd.kslot = (int)__float_as_uint(b.y);
+        cd.kx = a.y; cd.ky = a.z; cd.lawk = a.w; cd.thr = b.x; cd.kslot = blk ? (int)__float_as_uint(b.z) - slot_lo : (int)__float_as_uint(b.y);
         return cd;
     };
     auto bound_of = [&](int i) -> float {
@@ -237,7 +271,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             const float4 tq = sT[tid + j * NT];
             const int s = g + j * TPT;
             const float w = weight(tq, cd.k, cd.kx, cd.ky, cd.lawk);
-            const float sa = zero_after ? (float)src_offset(perm[s]) : fmaf(sgn, w, tq.x) + tq.y;
+            const float sa = zero_after ? (float)src_offset(tl[s]) : fmaf(sgn, w, tq.x) + tq.y;
             acc2 += ldiff<float>(Num<float>::lg2(col_factor(cK, sa, a, b)), Num<float>::lg2(col_factor(cK, tq.x + tq.y, a, b)));
         }
         if (own) acc2 += own_term(kj, cd.cur);
@@ -288,7 +322,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
         } else {
             for (int j = 0; j < ept; j++) {
                 const int s = g + j * TPT;
-                const double so = s < n ? src_offset(perm[s]) : 0.0;
+                const double so = s < nl ? src_offset(tl[s]) : 0.0;
                 const float hi = (float)so, lo = (float)(so - (double)hi);
                 *reinterpret_cast<float2 *>(&sT[tid + j * NT]) = make_float2(hi, lo);
             }
@@ -322,11 +356,12 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
 #pragma unroll
         for (int c = 0; c < SP; c++) {
             const float4 a = ring[((i + c) & (2 * RC - 1)) * 2];
-            const int kslot = (int)__float_as_uint(ring[((i + c) & (2 * RC - 1)) * 2 + 1].y);
+            const float4 rb = ring[((i + c) & (2 * RC - 1)) * 2 + 1];
+            const int kslot = blk ? (int)__float_as_uint(rb.z) - slot_lo : (int)__float_as_uint(rb.y);
             const uint32_t cur = __float_as_uint(a.x) >> 31;
             kk[c] = (int)(__float_as_uint(a.x) & 0x7fffffffu);
             kx[c] = a.y; ky[c] = a.z; lawk[c] = a.w; sgn[c] = cur ? -1.f : 1.f;
-            kj[c] = (kslot % TPT) == g ? kslot / TPT : 31;
+            kj[c] = (c < nc && (kslot % TPT) == g) ? kslot / TPT : 31;   // window entries past the list are zero records: no own cell
             zero[c] = (nocc + (cur ? -1 : 1)) == 0;
             pn[c] = 1.f; acc[c] = 0.f;
             // groups that can feel the candidate at the FP32 resolution of S_hi (2^-26 min S, with a margin for the drift
@@ -410,8 +445,8 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
     }
     for (int j = 0; j < ept; j++) {
         const int s = g + j * TPT;
-        if (s < n) {
-            const int q = perm[s];
+        if (s < nl) {
+            const int q = tl[s];
             const float4 tq = sT[tid + j * NT];
             St[q] = fmax(((double)tq.x + (double)tq.y) - src_offset(q), 0.0);
             yt[q] = (uint8_t)((ybits >> j) & 1u);
@@ -422,15 +457,44 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
         atomicAdd(&stats[MP_CNT_SCAN_EXEC], (unsigned long long)st_exec);
         atomicAdd(&stats[MP_CNT_SCAN_RETIRED], (unsigned long long)st_ret);
         atomicAdd(&stats[MP_CNT_SCAN_COMMIT], (unsigned long long)st_commit);
+        if (btasks && tid == 0 && rank == 0) atomicAdd(&stats[MP_CNT_SCAN_BLOCKS], 1ull);
     }
     if (CS > 1) cluster_barrier();
+}
+
+// Which (chain, year) tasks may be scanned block by block this sweep (mp_set_scan_blocks).  A block task leaves out every
+// target farther than the halo from its cell; that is the culled scan's own commit rule (weights below 2^-36 of the
+// target group's smallest S are not applied) as long as the largest weight at the halo distance, max_k A_k^b exp(-alpha halo),
+// stays below 2^-36 of the year's smallest S.  The year must also hold enough occupied patches that "the last occupied
+// patch left" (which the whole-task scan treats exactly) cannot arise while blocks change the count concurrently.
+// The decision depends on the task's own data only, so it is the same however the tasks are sharded over engines.
+static __global__ void __launch_bounds__(256)
+k_block_valid(const double *__restrict__ S, const mp_params *__restrict__ par, const int *__restrict__ count, int n, int ntrans,
+              int task_first, int task_stride, double halo, double log2_area_max, double log2_area_min, int *__restrict__ blockmode)
+{
+    __shared__ double s_min[8];
+    const int task = task_first + blockIdx.x * task_stride, c = task / ntrans;
+    const double *St = S + (size_t)task * n;
+    double m = 1e300;
+    for (int q = threadIdx.x; q < n; q += 256) m = fmin(m, St[q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) m = fmin(m, s_min[w]);
+        const double b = par[c].b, law = b >= 0.0 ? b * log2_area_max : b * log2_area_min;
+        const double wmax = exp2(law - par[c].alpha * halo * 1.4426950408889634);
+        blockmode[task] = (wmax < 1.4551915228366852e-11 * m && count[2 * task + 1] >= 64) ? 1 : 0;
+    }
 }
 
 }  // namespace mp
 
 #if defined(MP_FAST_GEOM) && defined(MP_FAST_HAS_POSITIONS)
 namespace mp {
-template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept)
+// nclusters whole (chain, year) tasks (btasks == nullptr) or block tasks of one colour
+template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept, int nclusters, const BlockTask *btasks)
 {
     constexpr int NT = TPT / CS;
     const size_t smem = (size_t)ept * NT * 16 + 2 * 32 * 32;   // targets + the two-chunk record ring
@@ -438,11 +502,9 @@ template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept)
     auto kern = k_sweep_y_cull<MP_FAST_GEOM, CS, TPT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    const int ntask_all = h->cfg.n_chains * (h->cfg.n_years - 1);
-    const int ntask = (ntask_all - h->task_first + h->task_stride - 1) / h->task_stride;
-    if (ntask <= 0) return MP_OK;
+    if (nclusters <= 0) return MP_OK;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(ntask * CS));
+    cfg.gridDim = dim3((unsigned)(nclusters * CS));
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
@@ -453,22 +515,29 @@ template <int CS, int TPT> static int launch_cull(mp_engine *h, int ept)
     CK(cudaLaunchKernelEx(&cfg, kern, view<float>(h), (const int *)h->d_perm, (const mp_params *)h->d_par,
                           (const uint8_t *)(h->have_era ? h->d_era : nullptr), (const uint8_t *)h->d_z, h->d_y, h->d_S[0],
                           (const CandRec *)h->d_cand, (const int *)h->d_cand_count, h->cfg.n_years, ept, (const int *)h->d_task_order,
-                          h->d_work));
+                          h->d_work, btasks, (const int *)h->d_tlist, (const int *)(h->blk_active ? h->d_blockmode : nullptr)));
     return MP_OK;
 }
-// culled variants exist for 512 threads per task (N up to 15,872) and the large-landscape geometries
-static int launch_cull_any(mp_engine *h, int cs, int tpt)
+// culled variants exist for 512 and 1024 threads per task (up to 31 slots per thread) and the large-landscape geometries
+static int launch_cull_any(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks_v)
 {
-    const int ept = (h->cfg.n_patches + tpt - 1) / tpt;
+    const BlockTask *btasks = (const BlockTask *)btasks_v;
+    const int ept = (nl_max + tpt - 1) / tpt;
     if (tpt == 512) switch (cs) {
-        case 1: return launch_cull<1, 512>(h, ept);
-        case 2: return launch_cull<2, 512>(h, ept);
-        case 4: return launch_cull<4, 512>(h, ept);
-        default: return launch_cull<8, 512>(h, ept);
+        case 1: return launch_cull<1, 512>(h, ept, nclusters, btasks);
+        case 2: return launch_cull<2, 512>(h, ept, nclusters, btasks);
+        case 4: return launch_cull<4, 512>(h, ept, nclusters, btasks);
+        default: return launch_cull<8, 512>(h, ept, nclusters, btasks);
     }
-    if (tpt == 2048) return launch_cull<8, 2048>(h, ept);
-    if (tpt == 4096) return cs == 16 ? launch_cull<16, 4096>(h, ept) : launch_cull<8, 4096>(h, ept);
-    if (tpt == 8192) return cs == 16 ? launch_cull<16, 8192>(h, ept) : launch_cull<8, 8192>(h, ept);
+    if (tpt == 1024) switch (cs) {
+        case 1: return launch_cull<1, 1024>(h, ept, nclusters, btasks);
+        case 2: return launch_cull<2, 1024>(h, ept, nclusters, btasks);
+        case 4: return launch_cull<4, 1024>(h, ept, nclusters, btasks);
+        default: return launch_cull<8, 1024>(h, ept, nclusters, btasks);
+    }
+    if (tpt == 2048) return launch_cull<8, 2048>(h, ept, nclusters, btasks);
+    if (tpt == 4096) return cs == 16 ? launch_cull<16, 4096>(h, ept, nclusters, btasks) : launch_cull<8, 4096>(h, ept, nclusters, btasks);
+    if (tpt == 8192) return cs == 16 ? launch_cull<16, 8192>(h, ept, nclusters, btasks) : launch_cull<8, 8192>(h, ept, nclusters, btasks);
     return MP_ERR_UNSUPPORTED;
 }
 }  // namespace mp

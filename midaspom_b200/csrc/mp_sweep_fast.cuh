@@ -27,7 +27,7 @@
 
 namespace mp {
 
-struct CandRec { uint32_t kinfo; float kx, ky, lawk, thr; uint32_t pad[3]; };   // 32 bytes; pad[0] = Morton slot of the patch
+struct CandRec { uint32_t kinfo; float kx, ky, lawk, thr; uint32_t pad[3]; };   // 32 bytes; pad[0] = layout (Morton) slot of the patch, pad[1] = its position in the visiting order
 
 // ------------------------------------------------------------------ cluster / DSMEM primitives
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -94,17 +94,18 @@ static __global__ void __launch_bounds__(1024)
 k_build_candidates(uint64_t seed, int chain_offset, uint32_t sweep, Landscape<float> ls, const float *__restrict__ aw,
                    const uint8_t *__restrict__ z, const uint8_t *__restrict__ y, CandRec *__restrict__ rec,
                    int *__restrict__ count /* [task][2]: candidates, occupied */, int T, int coords, int task_first, int task_stride,
-                   const int *__restrict__ perm /* Morton slot -> patch */)
+                   const int *__restrict__ scan /* visiting order: position -> patch */, const int *__restrict__ minv /* patch -> layout (Morton) slot */)
 {
     __shared__ int s_cnt[1024], s_occ[32];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x;
     const int task = task_first + blockIdx.x * task_stride, c = task / ntrans, t = task - c * ntrans;
     const uint8_t *zt = z + ((size_t)c * T + t) * n, *zn = zt + n, *yt = y + ((size_t)c * ntrans + t) * n;
-    // candidates are emitted in Morton-slot order (inv/perm are the identity without coordinates): consecutive candidates
-    // are spatial neighbours, which the culled scan exploits; any fixed visiting order is a valid Gibbs scan
+    // candidates are emitted in the visiting order of the scan (Morton order, block by block with a scan grid; the identity
+    // without coordinates): consecutive candidates are spatial neighbours, which the culled scan exploits; any fixed
+    // visiting order is a valid Gibbs scan
     const int per = (n + 1023) / 1024, s0 = min(n, tid * per), s1 = min(n, s0 + per);
     int cnt = 0, occ = 0;
-    for (int s = s0; s < s1; s++) { const int q = perm[s]; cnt += (zt[q] != 0 && zn[q] != 0); occ += (yt[q] != 0); }
+    for (int s = s0; s < s1; s++) { const int q = scan[s]; cnt += (zt[q] != 0 && zn[q] != 0); occ += (yt[q] != 0); }
     s_cnt[tid] = cnt;
     occ = (int)warp_sum_f((float)occ);
     if ((tid & 31) == 0) s_occ[tid >> 5] = occ;
@@ -118,14 +119,14 @@ k_build_candidates(uint64_t seed, int chain_offset, uint32_t sweep, Landscape<fl
     int off = s_cnt[tid] - cnt;
     CandRec *out = rec + (size_t)task * n;
     for (int s = s0; s < s1; s++) {
-        const int q = perm[s];
+        const int q = scan[s];
         if (!(zt[q] != 0 && zn[q] != 0)) continue;
         CandRec r;
         r.kinfo = (uint32_t)q | ((uint32_t)(yt[q] != 0) << 31);
         r.kx = coords ? ls.px[q] : 0.f; r.ky = coords ? ls.py[q] : 0.f;
         r.lawk = aw[(size_t)c * n + q];                 // FP32 engines keep log2 A^b (area_pre<float>)
         r.thr = (float)logit_u(rng(seed, (uint32_t)(chain_offset + c), sweep, RK_Y, (uint32_t)q, (uint32_t)t).x);
-        r.pad[0] = (uint32_t)s; r.pad[1] = r.pad[2] = 0;
+        r.pad[0] = (uint32_t)minv[q]; r.pad[1] = (uint32_t)s; r.pad[2] = 0;
         out[off++] = r;
     }
     if (tid == 1023) count[2 * task] = s_cnt[1023];

@@ -5,4 +5,4 @@
 #define MP_FAST_HAS_POSITIONS 1
 #include "mp_sweep_cull.cuh"
 int mp_launch_sweep_fast_coords(mp_engine *h, int cs, int tpt) { return mp::launch_fast_any(h, cs, tpt); }
-int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt) { return mp::launch_cull_any(h, cs, tpt); }
+int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks) { return mp::launch_cull_any(h, cs, tpt, nl_max, nclusters, btasks); }

@@ -187,6 +187,39 @@ class ShardedChain:
         self.eng.synchronize()
 
 
+def comm_init_from_torch(eng, group=None):
+    """Give the engine an NCCL communicator over the ranks of the torch.distributed job: rank 0 draws the unique id
+    (mp_comm_unique_id), torch.distributed only carries its 128 bytes, the communicator itself lives inside the library."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    eng.comm_init(world, rank, box[0])
+    return rank, world
+
+
+class NativeShardedChain:
+    """ShardedChain with the collectives inside the library (mp_sweep_sharded): all-gather of the owned connectivity
+    columns, broadcast of the owned year rows, no host synchronisation inside a sweep."""
+
+    def __init__(self, eng, group=None):
+        self.eng = eng
+        self.rank, self.world = comm_init_from_torch(eng, group)
+
+    def describe(self):
+        return (f"one chain over {self.world} GPUs: connectivity by target patches, y scan by years; all-gather of the owned "
+                "columns of S / S_prop and broadcast of the owned rows of y and S (NCCL inside libmidaspom_cuda.so, on the engine stream)")
+
+    def bytes_per_sweep(self):
+        C, T, N = self.eng.C, self.eng.T, self.eng.N
+        rows = C * (T - 1)
+        return rows * N * 8 * (1 + 1 / 16) + rows * N * 9          # S_prop columns every sweep (+ S every 16th); rows of S and y after the scan
+
+    def sweep(self, nsweeps=1):
+        self.eng.sweep_sharded(nsweeps)
+        self.eng.synchronize()
+
+
 def sweep_emulated_ranks(chains, nsweeps=1):
     """Run W ShardedChain objects that live in ONE process (one GPU) in lock step, summing their buffers
     directly instead of through NCCL -- the single-GPU emulation of the multi-rank path used by the tests."""

@@ -18,7 +18,7 @@ FP32, FP64 = 0, 1
 GEOM_LINEAR, GEOM_COORDS, GEOM_DENSE = 0, 1, 2
 NDRAW, NLSIG, NPART = 11, 8, 4
 KERNEL_CATEGORIES = ("conn", "col", "sweep_y", "sweep_z", "small", "sim")
-WORK_COUNTERS = ("scan_trips", "scan_exec", "scan_retired", "scan_commit", "scan_dense", "conn_exec", "conn_total", "gemm_tiles")
+WORK_COUNTERS = ("scan_trips", "scan_exec", "scan_retired", "scan_commit", "scan_dense", "conn_exec", "conn_total", "gemm_tiles", "scan_blocks")
 DRAW_FIELDS = ("e", "c", "alpha", "b", "p", "loglik", "n_y1", "n_z1", "K", "Ksrc", "dsrc")
 
 # every symbol include/libmidaspom_cuda.h declares
@@ -30,7 +30,9 @@ ABI_SYMBOLS = (
     "mp_flip_delta", "mp_init_chains", "mp_set_sampler", "mp_sweep", "mp_synchronize", "mp_num_draws",
     "mp_get_draws", "mp_reset_draws", "mp_sweep_index", "mp_simulate", "mp_device_ptr", "mp_set_timing",
     "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
-    "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry", "mp_get_conn_path",
+    "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry", "mp_get_conn_path", "mp_set_scan_blocks",
+    "mp_comm_unique_id", "mp_comm_init", "mp_comm_init_all", "mp_comm_destroy", "mp_comm_rank", "mp_comm_size", "mp_comm_last_error",
+    "mp_gather_draws", "mp_sweep_sharded", "mp_sweep_sharded_all",
 )
 
 
@@ -96,6 +98,16 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_set_landscape_dense.argtypes = [vp, dp, dp]
     L.mp_set_source_units.argtypes = [vp, dp]
     L.mp_get_scan_order.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.mp_set_scan_blocks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.mp_comm_unique_id.argtypes = [C.c_void_p]
+    L.mp_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+    L.mp_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    L.mp_comm_destroy.argtypes = [vp]
+    L.mp_comm_rank.argtypes = [vp]; L.mp_comm_size.argtypes = [vp]
+    L.mp_comm_last_error.restype = C.c_char_p
+    L.mp_gather_draws.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.mp_sweep_sharded.argtypes = [vp, C.c_int]
+    L.mp_sweep_sharded_all.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
     L.mp_set_observations.argtypes = [vp, i8p]
     L.mp_set_era.argtypes = [vp, u8p]
     L.mp_set_params.argtypes = [vp, pp]; L.mp_get_params.argtypes = [vp, pp]
@@ -201,6 +213,67 @@ class Engine:
     def set_source_units(self, src_unit=None):
         src_unit = self._f64(src_unit, (self.N,))
         self._ck(self.lib.mp_set_source_units(self.h, _p(src_unit, _dp)), "mp_set_source_units")
+
+    # ---- several GPUs behind the C ABI (NCCL inside the library)
+    COMM_ID_BYTES = 128
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """mp_comm_unique_id: the 128 bytes rank 0 hands to every rank of a communicator."""
+        buf = C.create_string_buffer(Engine.COMM_ID_BYTES)
+        rc = load_library().mp_comm_unique_id(buf)
+        if rc != 0:
+            raise MpError(f"mp_comm_unique_id failed ({rc}): {load_library().mp_comm_last_error().decode()}")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), Engine.COMM_ID_BYTES)
+        self._ck(self.lib.mp_comm_init(self.h, int(nranks), int(rank), buf), "mp_comm_init")
+
+    @staticmethod
+    def comm_init_all(engines):
+        """One process driving one engine per device: a communicator over all of them (mp_comm_init_all)."""
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        engines[0]._ck(engines[0].lib.mp_comm_init_all(arr, len(engines)), "mp_comm_init_all")
+
+    def comm_destroy(self):
+        self._ck(self.lib.mp_comm_destroy(self.h), "mp_comm_destroy")
+
+    def gather_draws(self, first=0, count=None) -> np.ndarray:
+        """mp_gather_draws: every rank's draws -> (ranks, sweeps, chains, NDRAW), the same on every rank."""
+        count = self.num_draws() - first if count is None else count
+        world = max(1, self.lib.mp_comm_size(self.h))
+        out = np.empty((world, count, self.C, NDRAW), dtype=np.float64)
+        self._ck(self.lib.mp_gather_draws(self.h, int(first), int(count), _p(out, _dp)), "mp_gather_draws")
+        return out
+
+    def sweep_sharded(self, nsweeps=1):
+        """mp_sweep_sharded: sweeps of the chains replicated on every rank of the communicator (asynchronous)."""
+        self._ck(self.lib.mp_sweep_sharded(self.h, int(nsweeps)), "mp_sweep_sharded")
+
+    @staticmethod
+    def sweep_sharded_all(engines, nsweeps=1):
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        engines[0]._ck(engines[0].lib.mp_sweep_sharded_all(arr, len(engines), int(nsweeps)), "mp_sweep_sharded_all")
+
+    def set_scan_blocks(self, nx: int, ny: int, k: int, halo: float):
+        """Block grid of the y scan (mp_set_scan_blocks): nx x ny cells, k x k colours, targets within `halo` of a cell."""
+        self._ck(self.lib.mp_set_scan_blocks(self.h, int(nx), int(ny), int(k), float(halo)), "mp_set_scan_blocks")
+
+    def set_scan_blocks_auto(self, px, py, alpha, s_min, area_pow_max=1.0, k=4, margin=1.15):
+        """Choose the finest grid the halo allows and install it.  The halo is the distance at which the largest dispersal
+        weight (area_pow_max = max_k A_k^b) falls below 2^-36 of the smallest connectivity s_min, times `margin` so that
+        the per-sweep validity check keeps holding while alpha and S move.  Returns (nx, ny, k, halo); (1, 1, 1, 0) when the
+        landscape is too small for more than one block."""
+        halo = margin * (36.0 * np.log(2.0) + np.log(max(area_pow_max, 1e-300) / max(s_min, 1e-300))) / float(alpha)
+        ex, ey = float(np.ptp(px)), float(np.ptp(py))
+        nx = max(1, int(np.floor((k - 1) * ex / (2.0 * halo) * 0.999)))
+        ny = max(1, int(np.floor((k - 1) * ey / (2.0 * halo) * 0.999)))
+        if nx * ny <= 1 or not np.isfinite(halo):
+            self.set_scan_blocks(1, 1, 1, 0.0)
+            return (1, 1, 1, 0.0)
+        self.set_scan_blocks(nx, ny, k, halo)
+        return (nx, ny, k, halo)
 
     def scan_order(self) -> np.ndarray:
         """Visiting order of the y scan (slot -> patch); Morton order for planar landscapes."""
@@ -395,7 +468,7 @@ class Engine:
     def scan_geometry(self):
         out = (C.c_int * 4)()
         self._ck(self.lib.mp_get_scan_geometry(self.h, out), "mp_get_scan_geometry")
-        return dict(threads_per_task=out[0], cluster=out[1], candidates_per_trip=out[2], culled=bool(out[3]))
+        return dict(threads_per_task=out[0], cluster=out[1], candidates_per_trip=out[2], culled=bool(out[3]), blocks=out[3] == 2)
 
     def probe_peaks(self):
         out = np.zeros(4)

@@ -66,12 +66,25 @@ static uint32_t morton_spread16(uint32_t v)
     v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
     return v;
 }
-typedef struct { uint32_t code; int32_t idx; } scan_key;
+typedef struct { uint32_t group, code; int32_t idx; } scan_key;
 static int scan_key_cmp(const void *a, const void *b)
 {
     const scan_key *x = a, *y = b;
+    if (x->group != y->group) return x->group < y->group ? -1 : 1;
     if (x->code != y->code) return x->code < y->code ? -1 : 1;
     return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+/* Block grid of the scan (blk_nx x blk_ny cells over the bounding box, blk_k x blk_k colours): cell and colour of a point.
+ * The scan visits colour by colour, block by block, Morton order inside a block; with a 1 x 1 grid this is the plain
+ * Morton order.  The engine (mp_set_scan_blocks) uses the identical arithmetic. */
+static inline int scan_cell(double v, double lo, double hi, int ncell)
+{
+    const double w = (hi - lo) / ncell;
+    if (!(w > 0.0)) return 0;
+    int c = (int)((v - lo) / w);
+    if (c < 0) c = 0;
+    if (c > ncell - 1) c = ncell - 1;
+    return c;
 }
 void spom_scan_order(const spom_model *m, int32_t *order)
 {
@@ -86,6 +99,7 @@ void spom_scan_order(const spom_model *m, int32_t *order)
     }
     double span = x1 - x0 > y1 - y0 ? x1 - x0 : y1 - y0;
     if (!(span > 1e-300)) span = 1e-300;
+    const int nbx = m->blk_nx > 1 ? m->blk_nx : 1, nby = m->blk_ny > 1 ? m->blk_ny : 1, bk = m->blk_k > 1 ? m->blk_k : 1;
     scan_key *key = malloc((size_t)n * sizeof *key);
     for (int k = 0; k < n; k++) {
         double fx = (m->px[k] - x0) / span * 65535.0, fy = (m->py[k] - y0) / span * 65535.0;
@@ -93,6 +107,8 @@ void spom_scan_order(const spom_model *m, int32_t *order)
         if (fy > 65535.0) fy = 65535.0;
         key[k].code = morton_spread16((uint32_t)fx) | (morton_spread16((uint32_t)fy) << 1);
         key[k].idx = k;
+        const int bx = scan_cell(m->px[k], x0, x1, nbx), by = scan_cell(m->py[k], y0, y1, nby);
+        key[k].group = (uint32_t)(((bx % bk) + bk * (by % bk)) * (nbx * nby) + by * nbx + bx);   /* (colour, block) */
     }
     qsort(key, (size_t)n, sizeof *key, scan_key_cmp);
     for (int s = 0; s < n; s++) order[s] = key[s].idx;

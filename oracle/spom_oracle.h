@@ -48,6 +48,7 @@ typedef struct {
     const double *src_unit;   /* external-source distance multipliers u_k, NULL => k+1 (loss.c:365) */
     const int8_t *obs;        /* T*n, years major: -1 missing, 0, 1 (piobs, main_MIDASPOM.c:152-161) */
     const uint8_t *era;       /* T-1 flags: 1 => pre-event transition (K, Ksrc apply); NULL => all 0 */
+    int32_t blk_nx, blk_ny, blk_k;   /* block grid of the y scan (spom_scan_order; 0 or 1 => one block: plain Morton order) */
 } spom_model;
 
 /* e, c: extinction / colonisation; alpha: 1/mean dispersal (flag -m); b: area exponent;
@@ -74,7 +75,8 @@ void   spom_rng(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t kind, ui
                 uint32_t out[4]);
 double spom_u01(uint32_t x);
 
-/* ---- visiting order of the y scan (Morton order of planar coordinates, else index order) ---- */
+/* ---- visiting order of the y scan: planar landscapes colour by colour, block by block of the blk_nx x blk_ny grid,
+ * Morton order inside a block (one block: plain Morton order); index order otherwise ---- */
 void   spom_scan_order(const spom_model *m, int32_t *order);
 
 /* ---- likelihood pieces ---- */

@@ -32,7 +32,7 @@ class SpomModel(C.Structure):
     _fields_ = [("n", C.c_int32), ("T", C.c_int32), ("geom", C.c_int32), ("detect", C.c_int32),
                 ("spacing", C.c_double), ("prior_occ", C.c_double),
                 ("px", _dp), ("py", _dp), ("dist", _dp), ("area", _dp), ("src_unit", _dp),
-                ("obs", _i8p), ("era", _u8p)]
+                ("obs", _i8p), ("era", _u8p), ("blk_nx", C.c_int32), ("blk_ny", C.c_int32), ("blk_k", C.c_int32)]
 
 
 class SpomParams(C.Structure):
@@ -103,7 +103,7 @@ class Model:
     """Owns the numpy arrays behind a spom_model struct."""
 
     def __init__(self, obs, geom=GEOM_LINEAR, spacing=100.0, prior_occ=0.5, detect=0, px=None, py=None,
-                 dist=None, area=None, src_unit=None, era=None):
+                 dist=None, area=None, src_unit=None, era=None, scan_blocks=(1, 1, 1)):
         self.obs = np.ascontiguousarray(obs, dtype=np.int8)
         self.T, self.n = self.obs.shape
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
@@ -112,7 +112,8 @@ class Model:
         self.geom, self.spacing, self.prior_occ, self.detect = geom, float(spacing), float(prior_occ), int(detect)
         self.c = SpomModel(self.n, self.T, geom, self.detect, self.spacing, self.prior_occ,
                            _ptr(self.px, _dp), _ptr(self.py, _dp), _ptr(self.dist, _dp), _ptr(self.area, _dp),
-                           _ptr(self.src_unit, _dp), _ptr(self.obs, _i8p), _ptr(self.era, _u8p))
+                           _ptr(self.src_unit, _dp), _ptr(self.obs, _i8p), _ptr(self.era, _u8p),
+                           int(scan_blocks[0]), int(scan_blocks[1]), int(scan_blocks[2]))
 
     def ref(self):
         return C.byref(self.c)
