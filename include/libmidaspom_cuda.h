@@ -192,13 +192,15 @@ int mp_simulate_ensemble(mp_engine *h, const mp_params *par_per_sim /* nsims */,
  * (compPePc, Pe.Pc, forward recursion): loglik_out[ie*nstep+ic] = log L(e_ie, c_ic) on the grid
  * ecmin + i*(ecmax-ecmin)/(nstep-1); ltot_out (nullable) = the "Total log-likelihood" of :414-425;
  * state_info (nullable, 4 ints) = variable patches, enumerated states, short-list states, max states/year.
- * Linear habitat only (flags -m -> a = 1/m, -d, -p, -s, -l, -u).  At most 24 variable patches. */
+ * Linear habitat only (flags -m -> a = 1/m, -d, -p, -s, -l, -u).  At most 24 variable patches, 12 missing cells in one
+ * year and 4,096 distinct observation-compatible rows (P is formed in 32 x 32 tiles, the grid in batches of <= 2 GB). */
 int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches, double a, double d, double prior_occ,
                        int nstep, double ecmin, double ecmax, double *loglik_out, double *ltot_out, int *state_info);
 /* MIDASPOM_dieoff.out (variant 1, main_MIDASPOM_dieoff.c:307-351) / MIDASPOM_loss.out (variant 2,
  * main_MIDASPOM_loss.c:345-386): likelihood of the FIRST survey row after ts pre-event + tdis post-event
  * unobserved years, on the log-spaced K grid (x the d_L grid for loss).  lik_out: nstepK (dieoff) or
- * nstepK*nstepd (loss) raw likelihoods, in the layout the reference writes.  At most 14 patches. */
+ * nstepK*nstepd (loss) raw likelihoods, in the layout the reference writes.  At most 16 patches (the reference's own
+ * 2^n x 2^n matrices stop fitting memory at 15); up to 13 the state vectors stay in shared memory. */
 int mp_exact_variant(int device, int variant, const int8_t *first_row, int n_patches, double a, double d, double prior_occ,
                      double eB, double cB, int ts, int tdis, int nstepK, double Kmin, double Kmax, int nstepd, double dmin,
                      double dmax, double *lik_out);

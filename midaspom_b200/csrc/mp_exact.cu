@@ -19,8 +19,10 @@
 // One deliberate difference: with -1 cells in the FIRST row the reference multiplies by a partly
 // uninitialised Pold (main_MIDASPOM.c:368-369,379).  Here Pold starts as the
 // identity -- the evident intent, and what the data-augmented likelihood sums to.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,7 +73,7 @@ static int build_tables(const int8_t *obs, int T, int n, float prioroc, Tables &
     for (int i = 0; i < T; i++) {                                                  // :222-279
         int s1 = 0;
         for (int j = 0; j < n; j++) if (obs[(size_t)i * n + j] == -1) s1++;
-        if (s1 > 20) { g_exact_error = "exact engine: more than 20 missing cells in one year"; return MP_ERR_UNSUPPORTED; }
+        if (s1 > 12) { g_exact_error = "exact engine: more than 12 missing cells in one year (4096 completions)"; return MP_ERR_UNSUPPORTED; }
         const uint32_t np = 1u << s1;
         tb.npstates[i] = (int)np;
         if (i == 0) tb.priorst.assign(np, 1.0f);
@@ -120,88 +122,101 @@ __global__ void k_exact_S(const uint32_t *__restrict__ masks, uint32_t nstates, 
 }
 
 constexpr int XCHUNK = 64;      // enumerated states per shared-memory chunk
-constexpr int XMAXID = 32;      // nextid <= 32 handled by the fused kernel (P held per thread pair)
+constexpr int XTILE = 32;       // P = Pe.Pc is formed in XTILE x XTILE tiles of short-list states (any number of them)
 
-// One CTA per grid point: P[i][i'] = sum_j Pe[i][j] Pc[j][i'] over all enumerated states j (ascending),
-// then the forward recursion of main_MIDASPOM.c:368-392 and Lik = log sum.
+// One CTA per (grid point, row tile, column tile): P[i][i'] = sum_j Pe[i][j] Pc[j][i'] over all enumerated states j
+// (ascending, the order of the reference's dgemm) for the short-list states i in the row tile and i' in the column tile.
 __global__ void __launch_bounds__(256)
-k_exact_grid(const uint32_t *__restrict__ masks, uint32_t nstates, int n, const double *__restrict__ S,
-             const uint32_t *__restrict__ short_masks, int nextid, const double *__restrict__ egrid,
-             const double *__restrict__ cgrid, int nstep, int T, const int *__restrict__ npstates,
-             const int *__restrict__ simpp_off, const uint32_t *__restrict__ simpp, const float *__restrict__ priorst,
-             double *__restrict__ Pout, double *__restrict__ lik, double *__restrict__ work)
+k_exact_P(const uint32_t *__restrict__ masks, uint32_t nstates, int n, const double *__restrict__ S,
+          const uint32_t *__restrict__ short_masks, int nextid, const double *__restrict__ egrid,
+          const double *__restrict__ cgrid, int nstep, int gp0, double *__restrict__ Pout)
 {
-    __shared__ double sPe[XCHUNK][XMAXID], sPc[XCHUNK][XMAXID];
-    const int gp = blockIdx.x, ie = gp / nstep, ic = gp - ie * nstep;
+    __shared__ double sPe[XCHUNK][XTILE], sPc[XCHUNK][XTILE];
+    const int gp = gp0 + blockIdx.x, ie = gp / nstep, ic = gp - ie * nstep;
+    const int a0 = blockIdx.y * XTILE, b0 = blockIdx.z * XTILE;
     double E = egrid[ie]; if (E > 1.0) E = 1.0;                                     // compPePc:21-22
     const double c = cgrid[ic];
     const int tid = threadIdx.x;
-    // each thread owns the entries tid, tid+256, ... of P (nextid^2 <= 1024)
-    constexpr int MAXOWN = (XMAXID * XMAXID + 255) / 256;
+    // each thread owns the entries tid, tid+256, ... of the tile
+    constexpr int MAXOWN = (XTILE * XTILE + 255) / 256;
     double acc[MAXOWN];
 #pragma unroll
     for (int o = 0; o < MAXOWN; o++) acc[o] = 0.0;
     for (uint32_t j0 = 0; j0 < nstates; j0 += XCHUNK) {
-        // factors of the chunk: thread handles (state, short state) pairs
-        for (int p = tid; p < XCHUNK * nextid; p += 256) {
-            const int js = p / nextid, i = p - js * nextid;
+        // factors of the chunk: thread handles (state, short state) pairs -- Pe for the row tile, Pc for the column tile
+        for (int p = tid; p < XCHUNK * XTILE * 2; p += 256) {
+            const int which = p / (XCHUNK * XTILE), r = p - which * (XCHUNK * XTILE);
+            const int js = r / XTILE, il = r - js * XTILE, i = (which ? b0 : a0) + il;
             const uint32_t j = j0 + js;
-            double pe = 0.0, pc = 0.0;
-            if (j < nstates) {
+            double v = 0.0;
+            if (j < nstates && i < nextid) {
                 const uint32_t y = masks[j], zs = short_masks[i];
                 if ((y & ~zs) == 0u) {                                              // compPePc:34-37  (0 -> 1 impossible)
-                    const int s1 = __popc(zs & ~y), s2 = __popc(zs & y);            // :38-39
-                    pe = pow(E, (double)s1) * pow(1.0 - E, (double)s2);             // :43
-                    pc = 1.0;
-                    for (int k = 0; k < n; k++) {                                   // :40
-                        if ((y >> k) & 1u) continue;
-                        double pC = c * S[(size_t)j * n + k];                       // :356-357
-                        if (pC > 1.0) pC = 1.0;
-                        pc *= ((zs >> k) & 1u) ? pC : 1.0 - pC;
+                    if (!which) {
+                        const int s1 = __popc(zs & ~y), s2 = __popc(zs & y);        // :38-39
+                        v = pow(E, (double)s1) * pow(1.0 - E, (double)s2);          // :43
+                    } else {
+                        v = 1.0;
+                        for (int k = 0; k < n; k++) {                               // :40
+                            if ((y >> k) & 1u) continue;
+                            double pC = c * S[(size_t)j * n + k];                   // :356-357
+                            if (pC > 1.0) pC = 1.0;
+                            v *= ((zs >> k) & 1u) ? pC : 1.0 - pC;
+                        }
                     }
                 }
             }
-            sPe[js][i] = pe; sPc[js][i] = pc;
+            (which ? sPc : sPe)[js][il] = v;
         }
         __syncthreads();
 #pragma unroll
         for (int o = 0; o < MAXOWN; o++) {
-            const int ent = tid + o * 256;
-            if (ent < nextid * nextid) {
-                const int a = ent / nextid, b = ent - a * nextid;
-                double s = acc[o];
-                for (int js = 0; js < XCHUNK; js++) s += sPe[js][a] * sPc[js][b];
-                acc[o] = s;
-            }
+            const int ent = tid + o * 256, al = ent / XTILE, bl = ent - al * XTILE;
+            double s = acc[o];
+            for (int js = 0; js < XCHUNK; js++) s += sPe[js][al] * sPc[js][bl];
+            acc[o] = s;
         }
         __syncthreads();
     }
-    double *P = Pout + (size_t)gp * nextid * nextid;
+    double *P = Pout + (size_t)blockIdx.x * nextid * nextid;
 #pragma unroll
-    for (int o = 0; o < MAXOWN; o++) { const int ent = tid + o * 256; if (ent < nextid * nextid) P[ent] = acc[o]; }
+    for (int o = 0; o < MAXOWN; o++) {
+        const int ent = tid + o * 256, ai = a0 + ent / XTILE, bi = b0 + ent % XTILE;
+        if (ai < nextid && bi < nextid) P[(size_t)ai * nextid + bi] = acc[o];
+    }
+}
+
+// One CTA per grid point: the forward recursion of main_MIDASPOM.c:368-392 over the years and Lik = log sum.
+// Pold (np0 x np_{t-1}) starts as the identity; the entries of each product are spread over the threads, every entry
+// summed in the reference's order.
+__global__ void __launch_bounds__(256)
+k_exact_forward(const double *__restrict__ Pall, int nextid, int T, const int *__restrict__ npstates, const int *__restrict__ simpp_off,
+                const uint32_t *__restrict__ simpp, const float *__restrict__ priorst, int maxnp, int gp0, double *__restrict__ lik,
+                double *__restrict__ work)
+{
+    const int tid = threadIdx.x, np0 = npstates[0];
+    const double *P = Pall + (size_t)blockIdx.x * nextid * nextid;
+    double *A = work + (size_t)blockIdx.x * 2 * np0 * maxnp, *B = A + (size_t)np0 * maxnp;
+    for (int p = tid; p < np0 * np0; p += 256) A[p] = (p / np0) == (p % np0) ? 1.0 : 0.0;
     __syncthreads();
-    if (tid != 0) return;
-    // forward recursion (:368-392); Pold (np0 x np_{t-1}) starts as the identity
-    int maxnp = 1;
-    for (int t = 0; t < T; t++) if (npstates[t] > maxnp) maxnp = npstates[t];
-    const int np0 = npstates[0];
-    double *A = work + (size_t)gp * 2 * np0 * maxnp, *B = A + (size_t)np0 * maxnp;
-    for (int k = 0; k < np0; k++) for (int l = 0; l < np0; l++) A[k * np0 + l] = k == l ? 1.0 : 0.0;
     for (int t = 1; t < T; t++) {
         const int npp = npstates[t - 1], npc = npstates[t];
         const uint32_t *sp = simpp + simpp_off[t - 1], *sc = simpp + simpp_off[t];
-        for (int k = 0; k < np0; k++)
-            for (int l = 0; l < npc; l++) {
-                double s = 0.0;
-                for (int m = 0; m < npp; m++) s += A[k * npp + m] * P[sp[m] * nextid + sc[l]];   // :375,379
-                B[k * npc + l] = s;
-            }
+        for (int p = tid; p < np0 * npc; p += 256) {
+            const int k = p / npc, l = p - k * npc;
+            double s = 0.0;
+            for (int m = 0; m < npp; m++) s += A[k * npp + m] * P[(size_t)sp[m] * nextid + sc[l]];   // :375,379
+            B[k * npc + l] = s;
+        }
+        __syncthreads();
         double *tmp = A; A = B; B = tmp;
     }
-    double L = 0.0;
-    const int npl = npstates[T - 1];
-    for (int k = 0; k < np0; k++) for (int l = 0; l < npl; l++) L += A[k * npl + l] * (double)priorst[k];   // :386-390
-    lik[gp] = log(L);                                                               // :392
+    if (tid == 0) {
+        double L = 0.0;
+        const int npl = npstates[T - 1];
+        for (int k = 0; k < np0; k++) for (int l = 0; l < npl; l++) L += A[k * npl + l] * (double)priorst[k];   // :386-390
+        lik[gp0 + blockIdx.x] = log(L);                                             // :392
+    }
 }
 
 
@@ -212,11 +227,13 @@ k_exact_grid(const uint32_t *__restrict__ masks, uint32_t nstates, int n, const 
 __global__ void __launch_bounds__(256)
 k_exact_variant(int n, const double *__restrict__ S, double a, double eB, double cB, const double *__restrict__ Kgrid,
                 const double *__restrict__ dgrid, int nd, int variant, int ts, int tdis, const uint32_t *__restrict__ pst,
-                const float *__restrict__ prior, int npst, double *__restrict__ lik)
+                const float *__restrict__ prior, int npst, double *__restrict__ lik,
+                double *__restrict__ gscratch /* 14..16 patches: the two state vectors of every CTA in global memory; else nullptr */)
 {
     extern __shared__ double xs[];
     const uint32_t nstates = 1u << n;
-    double *v = xs, *w = xs + nstates, *powE = w + nstates, *pow1 = powE + 32, *g = pow1 + 32;
+    double *v = gscratch ? gscratch + (size_t)blockIdx.x * 2 * nstates : xs, *w = v + nstates;
+    double *powE = gscratch ? xs : w + nstates, *pow1 = powE + 32, *g = pow1 + 32;
     const int iK = blockIdx.x / nd, id = blockIdx.x - iK * nd, tid = threadIdx.x;
     const double Kval = Kgrid[iK], dL = dgrid ? dgrid[id] : 0.0;
     for (uint32_t i = tid; i < nstates; i += 256) v[i] = 1.0;
@@ -280,7 +297,7 @@ int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches
     Tables tb;
     int rc = build_tables(obs, n_years, n_patches, (float)prior_occ, tb);
     if (rc != MP_OK) return rc;
-    if (tb.nextid > XMAXID) { g_exact_error = "exact engine: more than 32 distinct observation-compatible states"; return MP_ERR_UNSUPPORTED; }
+    if (tb.nextid > 4096) { g_exact_error = "exact engine: more than 4096 distinct observation-compatible states"; return MP_ERR_UNSUPPORTED; }
     const int n = n_patches, T = n_years, ng = nstep * nstep;
     // grid axes (:312-319): i*win + ecmin, last = ecmax
     const double win = (ecmax - ecmin) / (nstep - 1);
@@ -300,20 +317,24 @@ int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches
     if (state_info) { state_info[0] = tb.nvar; state_info[1] = (int)tb.nstates; state_info[2] = tb.nextid; state_info[3] = maxnp; }
 
     // one arena from the stream-ordered pool (kept by the driver between calls: no cudaMalloc / cudaFree per grid),
-    // carved into the 11 device buffers at 256-byte boundaries
+    // carved into the 11 device buffers at 256-byte boundaries.  P and the recursion's work space are held for a batch
+    // of grid points (at most ~2 GB), the grid is walked batch by batch.
     uint32_t *d_masks = nullptr, *d_short = nullptr, *d_simpp = nullptr;
     double *d_S = nullptr, *d_axis = nullptr, *d_P = nullptr, *d_lik = nullptr, *d_work = nullptr;
     int *d_np = nullptr, *d_off = nullptr;
     float *d_prior = nullptr;
     unsigned char *arena = nullptr;
+    const size_t per_point = ((size_t)tb.nextid * tb.nextid + (size_t)2 * tb.npstates[0] * maxnp) * 8;
+    const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)ng, ((size_t)2 << 30) / per_point));
+    const int ntile = (tb.nextid + XTILE - 1) / XTILE;
     XCK(cudaSetDevice(device));
     {
         size_t off = 0;
         auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
         const size_t o_masks = carve((size_t)tb.nstates * 4), o_short = carve((size_t)tb.nextid * 4), o_simpp = carve(simpp_flat.size() * 4),
                      o_S = carve((size_t)tb.nstates * n * 8), o_axis = carve((size_t)nstep * 8),
-                     o_P = carve((size_t)ng * tb.nextid * tb.nextid * 8), o_lik = carve((size_t)ng * 8),
-                     o_work = carve((size_t)ng * 2 * tb.npstates[0] * maxnp * 8), o_np = carve((size_t)T * 4),
+                     o_P = carve((size_t)batch * tb.nextid * tb.nextid * 8), o_lik = carve((size_t)ng * 8),
+                     o_work = carve((size_t)batch * 2 * tb.npstates[0] * maxnp * 8), o_np = carve((size_t)T * 4),
                      o_off = carve((size_t)(T + 1) * 4), o_prior = carve(tb.priorst.size() * 4);
         static bool pool_ready = false;
         if (!pool_ready) {                                // keep freed memory in the pool instead of returning it to the OS
@@ -335,9 +356,13 @@ int mp_exact_posterior(int device, const int8_t *obs, int n_years, int n_patches
     XCK(cudaMemcpyAsync(d_prior, tb.priorst.data(), tb.priorst.size() * 4, cudaMemcpyHostToDevice, 0));
     k_exact_S<<<(tb.nstates + 127) / 128, 128>>>(d_masks, tb.nstates, n, a, d, d_S);
     XCK(cudaGetLastError());
-    k_exact_grid<<<ng, 256>>>(d_masks, tb.nstates, n, d_S, d_short, tb.nextid, d_axis, d_axis, nstep, T, d_np, d_off, d_simpp,
-                              d_prior, d_P, d_lik, d_work);
-    XCK(cudaGetLastError());
+    for (int gp0 = 0; gp0 < ng; gp0 += batch) {
+        const int nb = std::min(batch, ng - gp0);
+        k_exact_P<<<dim3(nb, ntile, ntile), 256>>>(d_masks, tb.nstates, n, d_S, d_short, tb.nextid, d_axis, d_axis, nstep, gp0, d_P);
+        XCK(cudaGetLastError());
+        k_exact_forward<<<nb, 256>>>(d_P, tb.nextid, T, d_np, d_off, d_simpp, d_prior, maxnp, gp0, d_lik, d_work);
+        XCK(cudaGetLastError());
+    }
     XCK(cudaMemcpy(loglik_out, d_lik, (size_t)ng * 8, cudaMemcpyDeviceToHost));
     if (ltot_out) {                                                                 // :414-424 (host, nstep^2 terms)
         double Ltot = 0.0;
@@ -363,8 +388,8 @@ int mp_exact_variant(int device, int variant, const int8_t *first_row, int n_pat
                      double eB, double cB, int ts, int tdis, int nstepK, double Kmin, double Kmax, int nstepd, double dmin,
                      double dmax, double *lik_out)
 {
-    if (!first_row || !lik_out || n_patches < 1 || n_patches > 14 || nstepK < 2 || ts < 0 || tdis < 0 || (variant != 1 && variant != 2) ||
-        (variant == 2 && nstepd < 2)) { g_exact_error = "mp_exact_variant: bad argument (at most 14 patches)"; return MP_ERR_ARG; }
+    if (!first_row || !lik_out || n_patches < 1 || n_patches > 16 || nstepK < 2 || ts < 0 || tdis < 0 || (variant != 1 && variant != 2) ||
+        (variant == 2 && nstepd < 2)) { g_exact_error = "mp_exact_variant: bad argument (at most 16 patches)"; return MP_ERR_ARG; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_exact_error = "mp_exact_variant: no CUDA device; there is no CPU fallback"; return MP_ERR_CUDA; }
     const int n = n_patches, nd = variant == 2 ? nstepd : 1;
@@ -394,9 +419,13 @@ int mp_exact_variant(int device, int variant, const int8_t *first_row, int n_pat
     if (variant == 2) for (int i = 0; i < nd; i++) dg[i] = i * (dmax - dmin) / (nd - 1) + dmin;
     int rc = MP_OK;
     uint32_t *d_masks = nullptr, *d_pst = nullptr;
-    double *d_S = nullptr, *d_K = nullptr, *d_d = nullptr, *d_lik = nullptr;
+    double *d_S = nullptr, *d_K = nullptr, *d_d = nullptr, *d_lik = nullptr, *d_scr = nullptr;
     float *d_prior = nullptr;
-    const size_t smem = ((size_t)2 * nstates + 64 + 32) * sizeof(double);
+    // the two state vectors of a CTA fit its shared memory up to 13 patches (2 x 8,192 doubles); beyond that they live in
+    // global memory (MP_EXACT_GLOBAL=1 forces that path at any size)
+    const char *force = getenv("MP_EXACT_GLOBAL");
+    const bool global_vec = n > 13 || (force && atoi(force) != 0);
+    const size_t smem = ((global_vec ? 0 : (size_t)2 * nstates) + 64 + 32) * sizeof(double);
     XCK(cudaSetDevice(device));
     XCK(cudaMalloc(&d_masks, (size_t)nstates * 4)); XCK(cudaMalloc(&d_pst, (size_t)npst * 4)); XCK(cudaMalloc(&d_prior, (size_t)npst * 4));
     XCK(cudaMalloc(&d_S, (size_t)nstates * n * 8)); XCK(cudaMalloc(&d_K, (size_t)nstepK * 8)); XCK(cudaMalloc(&d_d, (size_t)nd * 8));
@@ -409,12 +438,13 @@ int mp_exact_variant(int device, int variant, const int8_t *first_row, int n_pat
     k_exact_S<<<(nstates + 127) / 128, 128>>>(d_masks, nstates, n, a, d, d_S);
     XCK(cudaGetLastError());
     XCK(cudaFuncSetAttribute(k_exact_variant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (global_vec) XCK(cudaMalloc(&d_scr, (size_t)nstepK * nd * 2 * nstates * 8));
     k_exact_variant<<<nstepK * nd, 256, smem>>>(n, d_S, a, eB, cB, d_K, variant == 2 ? d_d : nullptr, nd, variant, ts, tdis, d_pst,
-                                                d_prior, (int)npst, d_lik);
+                                                d_prior, (int)npst, d_lik, d_scr);
     XCK(cudaGetLastError());
     XCK(cudaMemcpy(lik_out, d_lik, (size_t)nstepK * nd * 8, cudaMemcpyDeviceToHost));
 done:
-    cudaFree(d_masks); cudaFree(d_pst); cudaFree(d_prior); cudaFree(d_S); cudaFree(d_K); cudaFree(d_d); cudaFree(d_lik);
+    cudaFree(d_masks); cudaFree(d_pst); cudaFree(d_prior); cudaFree(d_S); cudaFree(d_K); cudaFree(d_d); cudaFree(d_lik); cudaFree(d_scr);
     return rc;
 }
 

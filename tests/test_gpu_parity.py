@@ -173,6 +173,39 @@ def test_exact_engine_reproduces_reference_posterior_tables(golden, example_obs)
     np.testing.assert_allclose(ll3, golden["loglik_s3_survey"], rtol=0, atol=2e-12)
 
 
+def test_exact_engine_on_wide_inputs_matches_the_reference():
+    """More than 32 distinct observation-compatible rows (P tiled over the short list) and a year with 6 missing cells
+    (64 completions): the posterior tables the reference binary printed for these inputs (tests/golden/make_golden_wide.py)."""
+    from pathlib import Path
+    g = dict(np.load(Path(__file__).resolve().parent / "golden" / "golden_wide.npz"))
+    for tag, nstep, min_next in (("a", 21, 70), ("b", 11, 34)):
+        obs, tab, want_ltot = g[f"wide_{tag}_obs"].astype(np.int8), g[f"wide_{tag}_post"], float(g[f"wide_{tag}_ltot"])
+        ll, ltot, info = mb.exact_posterior(obs, a=A, d=100.0, prior_occ=0.5, nstep=nstep, ecmin=0.0, ecmax=1.0)
+        assert info["nextid"] >= min_next, info
+        assert abs(ltot - want_ltot) < 6e-6                                              # printed with %.5lf
+        np.testing.assert_allclose(np.exp(ll - ltot), tab, rtol=1e-9, atol=5.1e-21)
+    # the oracle's forward recursion agrees too, at full double precision
+    m = O.Model(g["wide_a_obs"].astype(np.int8), spacing=100.0, prior_occ=0.5)
+    ll, _, _ = mb.exact_posterior(g["wide_a_obs"].astype(np.int8), a=A, d=100.0, nstep=3, ecmin=0.2, ecmax=0.8)
+    want = np.array([[O.marginal_loglik(m, O.params(e=e, c=c, alpha=A)) for c in (0.2, 0.5, 0.8)] for e in (0.2, 0.5, 0.8)])
+    rel_close(ll, want, 1e-10, floor=1.0)
+
+
+def test_exact_variant_beyond_shared_memory(monkeypatch, example_obs):
+    """14-16 patches keep the two state vectors in global memory: the same code path forced on the bundled example must
+    reproduce the shared-memory result bit for bit, and a 14-patch row must run and give a likelihood in (0, 1]."""
+    small = mb.exact_variant("dieoff", example_obs[0], 0.71, 0.52, ts=6, tdis=4, a=A, d=100.0, nstepK=9)
+    monkeypatch.setenv("MP_EXACT_GLOBAL", "1")
+    forced = mb.exact_variant("dieoff", example_obs[0], 0.71, 0.52, ts=6, tdis=4, a=A, d=100.0, nstepK=9)
+    assert (small == forced).all()
+    monkeypatch.delenv("MP_EXACT_GLOBAL")
+    row = np.array([1, 0, 1, 1, -1, 0, 1, 0, 0, 1, 1, 0, -1, 1], dtype=np.int8)
+    big = mb.exact_variant("loss", row, 0.5, 0.3, ts=3, tdis=2, a=A, d=100.0, nstepK=3, nstepd=2)
+    assert big.shape == (3, 2) and np.isfinite(big).all() and (big > 0).all() and (big <= 1).all()
+    with pytest.raises(mb.MpError):
+        mb.exact_variant("dieoff", np.ones(17, dtype=np.int8), 0.5, 0.3, ts=1, tdis=1)
+
+
 def test_exact_variants_reproduce_dieoff_and_loss_outputs(golden, example_obs):
     """run_examples.sh:11,14 -- `MIDASPOM_dieoff.out -a 10 -e 0.71 -c 0.52 -m 400 -d 100 -s 151` (151 values) and
     `MIDASPOM_loss.out ... -s 7 -v 3` (7 x 3): vector propagation here vs matrix powers there."""

@@ -2,6 +2,7 @@
 reference binaries / functions (tests/golden/golden.npz, see make_golden.py) and, when oracle/_ref
 was built in this container, live calls into the reference's own functions."""
 import ctypes as C
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -210,3 +211,18 @@ def test_simulator_matches_simpij_distribution(golden):
     freq = acc / nsim
     se = np.sqrt(golden["simpij_freq"] * (1 - golden["simpij_freq"]) * (1 / nsim + 1 / int(golden["simpij_nsim"])))
     assert (np.abs(freq - golden["simpij_freq"]) < 4.5 * se + 1e-9).all()
+
+
+def test_marginal_loglik_matches_reference_on_wide_inputs():
+    """Inputs beyond the bundled example, run through the reference binary by tests/golden/make_golden_wide.py: a year with 6
+    missing cells (64 completions) and a 45-year record with more than 32 distinct rows.  The oracle's marginal likelihood
+    reproduces the posterior table the reference printed (density = exp(loglik - ltot))."""
+    g = dict(np.load(Path(__file__).resolve().parent / "golden" / "golden_wide.npz"))
+    for tag, nstep in (("a", 21), ("b", 11)):
+        obs, tab, ltot = g[f"wide_{tag}_obs"].astype(np.int8), g[f"wide_{tag}_post"], float(g[f"wide_{tag}_ltot"])
+        m = O.Model(obs, spacing=100.0, prior_occ=0.5)
+        axis = np.linspace(0.0, 1.0, nstep)
+        for ie, ic in ((nstep // 2, nstep // 2), (3, 7), (nstep - 2, 1), (1, nstep - 2)):
+            ll = O.marginal_loglik(m, O.params(e=axis[ie], c=axis[ic], alpha=1.0 / 400))
+            # ltot is printed with 5 decimals: exp(ll - ltot) carries a relative error of up to 5e-6 from it
+            assert abs(np.exp(ll - ltot) - tab[ie, ic]) <= 6e-6 * tab[ie, ic] + 5.1e-21, (tag, ie, ic)
