@@ -13,6 +13,11 @@
  *   -c CHAINS   chains (default 8)      -b BURNIN  sweeps discarded (default SWEEPS/5)
  *   -r SEED     Philox seed (default 1) -g DEVICE  CUDA ordinal (default 0)
  *   -t FILE     also write the raw draws (one row per sweep and chain)
+ *   -G 0,1,2,3  run the chains on several GPUs: the drop-in for `mpirun -np 4 MIDASPOM_MPI.out` (run_examples_MPI.sh:8).
+ *               Where MIDASPOM_MPI splits the rows of the (e, c) grid over ranks and rank 0 collects them with MPI_Send /
+ *               MPI_Recv (main_MIDASPOM_MPI.c:361-372,483-505), the chains are split over the listed devices (device g
+ *               holds the global chains g*C/G ... ), sweep concurrently, and one NCCL all-gather inside the library
+ *               (mp_comm_init_all + mp_gather_draws_all) brings the draws together.  Needs -n.
  */
 #include <math.h>
 #include <stdio.h>
@@ -46,30 +51,46 @@ static int run_grid(const int8_t *obs, int tmax, int n, double a, double d, floa
     return 0;
 }
 
+#define MAXDEV 16
 static int run_mcmc(const int8_t *obs, int tmax, int n, double a, double d, float prioroc, int nstep, double ecmin,
-                    double ecmax, int device, const char *fout, int nsweeps, int nchains, int burn, unsigned long long seed,
+                    double ecmax, const int *devices, int ndev, const char *fout, int nsweeps, int nchains, int burn, unsigned long long seed,
                     const char *fdraws)
 {
-    mp_config cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.n_patches = n; cfg.n_years = tmax; cfg.n_chains = nchains; cfg.precision = MP_FP64; cfg.device = device;
-    cfg.max_draws = nsweeps; cfg.seed = seed; cfg.prior_occ = prioroc;
-    mp_engine *h = NULL;
-    if (mp_create(&cfg, &h) != MP_OK) { fprintf(stderr, "mp_create: %s\n", mp_last_error(NULL)); return 2; }
+    const int cpg = nchains / ndev;                                   /* chains per GPU (main checked divisibility) */
+    mp_engine *hs[MAXDEV] = { NULL };
     int rc = 2;
     mp_sampler_config sc;
     memset(&sc, 0, sizeof sc);
     sc.e_min = ecmin; sc.e_max = ecmax; sc.c_min = ecmin; sc.c_max = ecmax;     /* uniform prior on the grid's square (:312-319) */
     sc.alpha_min = a; sc.alpha_max = a; sc.b_min = 0; sc.b_max = 0; sc.p_min = 1; sc.p_max = 1;
     sc.sample_e = 1; sc.sample_c = 1; sc.n_e_steps = 4; sc.n_c_steps = 2; sc.n_adapt = burn; sc.update_z = 1; sc.update_y = 1;
-    mp_params *par = (mp_params *)calloc((size_t)nchains, sizeof(mp_params));
-    for (int c = 0; c < nchains; c++) { par[c].e = 0.5 * (ecmin + ecmax); par[c].c = 0.5 * (ecmin + ecmax); par[c].alpha = a; par[c].p = 1; par[c].K = 1; }
+    mp_params *par = (mp_params *)calloc((size_t)cpg, sizeof(mp_params));
+    for (int c = 0; c < cpg; c++) { par[c].e = 0.5 * (ecmin + ecmax); par[c].c = 0.5 * (ecmin + ecmax); par[c].alpha = a; par[c].p = 1; par[c].K = 1; }
+    /* draws of all chains, [sweep][global chain][MP_NDRAW]; gathered per device as [device][sweep][local chain] first */
+    double *gath = (double *)malloc((size_t)nsweeps * nchains * MP_NDRAW * sizeof(double));
     double *draws = (double *)malloc((size_t)nsweeps * nchains * MP_NDRAW * sizeof(double));
     double *dens = (double *)calloc((size_t)nstep * nstep, sizeof(double));
-    if (mp_set_landscape_linear(h, d, NULL) || mp_set_source_units(h, NULL) || mp_set_observations(h, obs) ||
-        mp_set_params(h, par) || mp_init_chains(h, &sc, 1)) { fprintf(stderr, "setup: %s\n", mp_last_error(h)); goto out; }
-    printf("Starting MCMC: %d chains x %d sweeps (%d burn-in)\n", nchains, nsweeps, burn);
-    if (mp_sweep(h, nsweeps) || mp_synchronize(h) || mp_get_draws(h, 0, nsweeps, draws)) { fprintf(stderr, "sweep: %s\n", mp_last_error(h)); goto out; }
+    for (int g = 0; g < ndev; g++) {
+        mp_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.n_patches = n; cfg.n_years = tmax; cfg.n_chains = cpg; cfg.chain_offset = g * cpg; cfg.precision = MP_FP64; cfg.device = devices[g];
+        cfg.max_draws = nsweeps; cfg.seed = seed; cfg.prior_occ = prioroc;
+        if (mp_create(&cfg, &hs[g]) != MP_OK) { fprintf(stderr, "mp_create (device %d): %s\n", devices[g], mp_last_error(NULL)); goto out; }
+        if (mp_set_landscape_linear(hs[g], d, NULL) || mp_set_source_units(hs[g], NULL) || mp_set_observations(hs[g], obs) ||
+            mp_set_params(hs[g], par) || mp_init_chains(hs[g], &sc, 1)) { fprintf(stderr, "setup: %s\n", mp_last_error(hs[g])); goto out; }
+    }
+    if (ndev > 1 && mp_comm_init_all(hs, ndev)) { fprintf(stderr, "mp_comm_init_all: %s %s\n", mp_last_error(hs[0]), mp_comm_last_error()); goto out; }
+    printf("Starting MCMC: %d chains x %d sweeps (%d burn-in) on %d GPU%s\n", nchains, nsweeps, burn, ndev, ndev > 1 ? "s" : "");
+    for (int g = 0; g < ndev; g++)                                    /* asynchronous: the devices sweep concurrently */
+        if (mp_sweep(hs[g], nsweeps)) { fprintf(stderr, "sweep: %s\n", mp_last_error(hs[g])); goto out; }
+    for (int g = 0; g < ndev; g++) if (mp_synchronize(hs[g])) { fprintf(stderr, "sweep: %s\n", mp_last_error(hs[g])); goto out; }
+    if (ndev > 1) {
+        if (mp_gather_draws_all(hs, ndev, 0, nsweeps, gath)) { fprintf(stderr, "gather: %s\n", mp_last_error(hs[0])); goto out; }
+        for (int g = 0; g < ndev; g++)
+            for (int s = 0; s < nsweeps; s++)
+                memcpy(draws + ((size_t)s * nchains + (size_t)g * cpg) * MP_NDRAW, gath + (((size_t)g * nsweeps + s) * cpg) * MP_NDRAW,
+                       (size_t)cpg * MP_NDRAW * sizeof(double));
+    } else if (mp_get_draws(hs[0], 0, nsweeps, draws)) { fprintf(stderr, "draws: %s\n", mp_last_error(hs[0])); goto out; }
     {
         /* histogram on the reference's grid: node i collects draws within half a window, edge nodes half
          * as wide -- the cells the trapezoid weights of :418-421 stand for */
@@ -109,8 +130,8 @@ static int run_mcmc(const int8_t *obs, int tmax, int n, double a, double d, floa
     }
     rc = 0;
 out:
-    free(par); free(draws); free(dens);
-    mp_destroy(h);
+    free(par); free(draws); free(gath); free(dens);
+    for (int g = 0; g < ndev; g++) if (hs[g]) mp_destroy(hs[g]);
     return rc;
 }
 
@@ -122,8 +143,9 @@ int main(int argc, char **argv)
     double d = 100, a = 1.0 / 400, ecmin = 0.0, ecmax = 1.0;
     int nstep = 101, nsweeps = 0, nchains = 8, burn = -1, device = 0, c;
     unsigned long long seed = 1;
+    int devices[MAXDEV], ndev = 0;
     opterr = 0;
-    while ((c = getopt(argc, argv, "m:p:d:i:o:s:l:u:n:c:b:r:g:t:")) != -1)
+    while ((c = getopt(argc, argv, "m:p:d:i:o:s:l:u:n:c:b:r:g:t:G:")) != -1)
         switch (c) {
         case 'm': a = 1.0 / atof(optarg); break;
         case 'p': prioroc = (float)atof(optarg); break;
@@ -139,9 +161,14 @@ int main(int argc, char **argv)
         case 'r': seed = strtoull(optarg, NULL, 10); break;
         case 'g': device = atoi(optarg); break;
         case 't': fdraws = optarg; break;
+        case 'G':
+            for (char *tok = strtok(optarg, ","); tok && ndev < MAXDEV; tok = strtok(NULL, ",")) devices[ndev++] = atoi(tok);
+            break;
         default: fprintf(stderr, "Unknown option `-%c'.\n", optopt); return 1;
         }
     if (nstep < 2) { fprintf(stderr, "-s must be at least 2\n"); return 1; }
+    if (ndev == 0) { devices[0] = device; ndev = 1; }
+    if (ndev > 1 && (nsweeps <= 0 || nchains % ndev)) { fprintf(stderr, "-G needs -n SWEEPS and a chain count divisible by the number of GPUs\n"); return 1; }
     const double win = (ecmax - ecmin) / (nstep - 1);
     printf("Parameters for numerical approximation of the posterior density:\n\tWindow size=%lf, number of steps=%d\n", win, nstep);
     time_t start = time(NULL);
@@ -172,8 +199,8 @@ int main(int argc, char **argv)
     int rc;
     if (nsweeps > 0) {
         if (burn < 0) burn = nsweeps / 5;
-        rc = run_mcmc(obs, tmax, n, a, d, prioroc, nstep, ecmin, ecmax, device, fout, nsweeps, nchains, burn, seed, fdraws);
-    } else rc = run_grid(obs, tmax, n, a, d, prioroc, nstep, ecmin, ecmax, device, fout);
+        rc = run_mcmc(obs, tmax, n, a, d, prioroc, nstep, ecmin, ecmax, devices, ndev, fout, nsweeps, nchains, burn, seed, fdraws);
+    } else rc = run_grid(obs, tmax, n, a, d, prioroc, nstep, ecmin, ecmax, devices[0], fout);
     free(obs);
     printf(" Total running time: %.2lf min\n", difftime(time(NULL), start) / 60.0);
     return rc;

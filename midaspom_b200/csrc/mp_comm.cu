@@ -181,4 +181,39 @@ int mp_gather_draws(mp_engine *h, int first, int count, double *out)
     return MP_OK;
 }
 
+// The same gather for one process driving all engines of the communicator (mp_comm_init_all): the all-gathers of the
+// local engines form one NCCL group; out (host) receives the copy assembled on engines[0].
+int mp_gather_draws_all(mp_engine **hs, int n, int first, int count, double *out)
+{
+    if (!hs || n < 1 || !hs[0] || !out) return MP_ERR_ARG;
+    mp_engine *h = hs[0];
+    const size_t row = nC(h) * MP_NDRAW * 8, bytes = (size_t)count * row;
+    for (int i = 0; i < n; i++) {
+        REQUIRE(hs[i] && hs[i]->comm && hs[i]->comm_size == n, MP_ERR_STATE, "mp_gather_draws_all: every engine needs the communicator of mp_comm_init_all");
+        REQUIRE(hs[i]->cfg.n_chains == h->cfg.n_chains, MP_ERR_ARG, "mp_gather_draws_all: all engines must hold the same number of chains");
+        REQUIRE(first >= 0 && count >= 0 && first + count <= hs[i]->ndraws, MP_ERR_ARG, "mp_gather_draws_all: range outside recorded draws");
+    }
+    if (bytes == 0) return MP_OK;
+    std::vector<void *> d_all(n, nullptr);
+    int rc = MP_OK;
+    for (int i = 0; i < n && rc == MP_OK; i++) {
+        if (cudaSetDevice(hs[i]->cfg.device) != cudaSuccess || cudaMalloc(&d_all[i], bytes * (size_t)n) != cudaSuccess) { h->err = "mp_gather_draws_all: cudaMalloc failed"; rc = MP_ERR_CUDA; }
+    }
+    if (rc == MP_OK) {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int i = 0; i < n && r == ncclSuccess; i++)
+            r = g_nccl.AllGather((const char *)hs[i]->d_draws + (size_t)first * row, d_all[i], bytes, ncclChar, (ncclComm_t)hs[i]->comm, hs[i]->stream);
+        const ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) { h->err = std::string("mp_gather_draws_all: ") + g_nccl.GetErrorString(r); rc = MP_ERR_CUDA; }
+    }
+    for (int i = 0; i < n && rc == MP_OK; i++) {
+        cudaSetDevice(hs[i]->cfg.device);
+        if (i == 0 && cudaMemcpyAsync(out, d_all[0], bytes * (size_t)n, cudaMemcpyDeviceToHost, hs[0]->stream) != cudaSuccess) rc = MP_ERR_CUDA;
+        if (cudaStreamSynchronize(hs[i]->stream) != cudaSuccess) { h->err = "mp_gather_draws_all: stream error"; rc = MP_ERR_CUDA; }
+    }
+    for (int i = 0; i < n; i++) if (d_all[i]) { cudaSetDevice(hs[i]->cfg.device); cudaFree(d_all[i]); }
+    return rc;
+}
+
 }  // extern "C"

@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
     "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry", "mp_get_conn_path", "mp_set_scan_blocks",
     "mp_comm_unique_id", "mp_comm_init", "mp_comm_init_all", "mp_comm_destroy", "mp_comm_rank", "mp_comm_size", "mp_comm_last_error",
-    "mp_gather_draws", "mp_sweep_sharded", "mp_sweep_sharded_all",
+    "mp_gather_draws", "mp_gather_draws_all", "mp_debug_counters", "mp_sweep_sharded", "mp_sweep_sharded_all",
 )
 
 
@@ -106,6 +106,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_comm_rank.argtypes = [vp]; L.mp_comm_size.argtypes = [vp]
     L.mp_comm_last_error.restype = C.c_char_p
     L.mp_gather_draws.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.mp_gather_draws_all.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, dp]
     L.mp_sweep_sharded.argtypes = [vp, C.c_int]
     L.mp_sweep_sharded_all.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
     L.mp_set_observations.argtypes = [vp, i8p]
@@ -133,6 +134,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
     L.mp_probe_peaks.argtypes = [vp, dp]
     L.mp_get_work_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
+    L.mp_debug_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mp_get_scan_geometry.argtypes = [vp, C.POINTER(C.c_int)]
     L.mp_get_conn_path.argtypes = [vp]
     L.mp_exact_posterior.argtypes = [C.c_int, i8p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
@@ -245,6 +247,16 @@ class Engine:
         world = max(1, self.lib.mp_comm_size(self.h))
         out = np.empty((world, count, self.C, NDRAW), dtype=np.float64)
         self._ck(self.lib.mp_gather_draws(self.h, int(first), int(count), _p(out, _dp)), "mp_gather_draws")
+        return out
+
+    @staticmethod
+    def gather_draws_all(engines, first=0, count=None) -> np.ndarray:
+        """mp_gather_draws_all: one process driving all engines of the communicator -> (engines, sweeps, chains, NDRAW)."""
+        e0 = engines[0]
+        count = e0.num_draws() - first if count is None else count
+        out = np.empty((len(engines), count, e0.C, NDRAW), dtype=np.float64)
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        e0._ck(e0.lib.mp_gather_draws_all(arr, len(engines), int(first), int(count), _p(out, _dp)), "mp_gather_draws_all")
         return out
 
     def sweep_sharded(self, nsweeps=1):
@@ -460,6 +472,11 @@ class Engine:
         out = (C.c_uint64 * len(WORK_COUNTERS))()
         self._ck(self.lib.mp_get_work_counters(self.h, out, int(reset)), "mp_get_work_counters")
         return dict(zip(WORK_COUNTERS, [int(v) for v in out]))
+
+    def debug_counters(self):
+        out = (C.c_uint64 * 16)()
+        self._ck(self.lib.mp_debug_counters(self.h, out), "mp_debug_counters")
+        return [int(v) for v in out]
 
     def conn_path(self):
         """Kernel that evaluated the connectivity last: "k_conn" or "gemm" (tcgen05 contraction for chains sharing alpha, b)."""
