@@ -228,8 +228,6 @@ int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset);
 enum { MP_CNT_SCAN_TRIPS = 0, MP_CNT_SCAN_EXEC = 1, MP_CNT_SCAN_RETIRED = 2, MP_CNT_SCAN_COMMIT = 3, MP_CNT_SCAN_DENSE = 4,
        MP_CNT_CONN_EXEC = 5, MP_CNT_CONN_TOTAL = 6, MP_CNT_GEMM_TILES = 7, MP_CNT_SCAN_BLOCKS = 8, MP_CNT_N = 9 };
 int mp_get_work_counters(mp_engine *h, uint64_t *out /* MP_CNT_N */, int reset);
-/* 16 profiling slots of the windowed scan (cycles per phase, event counts): zero unless the library was built with -DMP_WPC_PROFILE */
-int mp_debug_counters(mp_engine *h, uint64_t *out16);
 /* which kernel evaluated the connectivity last: 0 = k_conn (per-chain parameters, FP64 accumulation), 1 = the tensor-core
  * contraction k_conn_gemm (FP32 engines; taken by mp_connectivity / mp_loglik / mp_loglik_host when every chain holds the
  * same alpha and b as uploaded by mp_set_params, the matrix form c*M%*%pti of Rscript/simuls_traj.R:16,203,214) */

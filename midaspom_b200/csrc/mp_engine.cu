@@ -194,12 +194,6 @@ static int launch_sweep_y_fast(mp_engine *h)
     // exact spatial culling of the evaluation (mp_sweep_cull.cuh) where positions exist and the landscape is large
     const bool culled = h->fast_cull && h->geom != MP_GEOM_DENSE && tpt >= 512;
     h->last_scan[0] = tpt; h->last_scan[1] = cs; h->last_scan[2] = culled ? (tpt > 1024 ? 4 : 2) : 1; h->last_scan[3] = culled;
-    // windowed one-CTA scan (mp_sweep_wpc.cuh) where the targets of a task fit one CTA's shared memory
-    const bool wpc_whole = culled && h->use_wpc && mp_wpc_smem_bytes(n) <= 227 * 1024;
-    auto launch_wpc = [&](int nl_max, int nclusters, const void *bt) {
-        return h->geom == MP_GEOM_LINEAR ? mp_launch_sweep_wpc_linear(h, h->wpc_window, nl_max, nclusters, bt)
-                                         : mp_launch_sweep_wpc_coords(h, h->wpc_window, nl_max, nclusters, bt);
-    };
     if (culled && h->blk_active) {
         // block grid: decide per task whether its halo suffices this sweep, scan those tasks colour by colour (the blocks of
         // one colour concurrently), then the remaining tasks as whole years (clusters of the other kind return at once)
@@ -216,19 +210,12 @@ static int launch_sweep_y_fast(mp_engine *h)
             const size_t ept = (size_t)(h->blk_nl_max + btpt - 1) / btpt;
             while (bcs < 8 && ept * (size_t)(btpt / bcs) * 16 + 2048 > 227 * 1024) bcs *= 2;
         }
-        const bool wpc_blk = h->use_wpc && mp_wpc_smem_bytes(h->blk_nl_max) <= 227 * 1024;
         h->last_scan[0] = btpt; h->last_scan[1] = bcs; h->last_scan[2] = btpt > 1024 ? 4 : 2; h->last_scan[3] = 2;
-        if (wpc_blk) { h->last_scan[0] = 512; h->last_scan[1] = 1; h->last_scan[2] = h->wpc_window; }
         for (size_t col = 0; col < h->colour_n.size(); col++) {
             if (h->colour_n[col] == 0) continue;
             const void *bt = (const char *)h->d_btasks + (size_t)h->colour_off[col] * sizeof(mp::BlockTask);
-            if ((rc = wpc_blk ? launch_wpc(h->blk_nl_max, h->colour_n[col], bt)
-                              : mp_launch_sweep_cull_coords(h, bcs, btpt, h->blk_nl_max, h->colour_n[col], bt)) != MP_OK) return rc;
+            if ((rc = mp_launch_sweep_cull_coords(h, bcs, btpt, h->blk_nl_max, h->colour_n[col], bt)) != MP_OK) return rc;
         }
-    }
-    if (wpc_whole) {
-        if (!h->blk_active) { h->last_scan[0] = 512; h->last_scan[1] = 1; h->last_scan[2] = h->wpc_window; h->last_scan[3] = 1; }
-        return launch_wpc(n, ntask_own, nullptr);
     }
     if (culled)
         return h->geom == MP_GEOM_LINEAR ? mp_launch_sweep_cull_linear(h, cs, tpt, n, ntask_own, nullptr)
@@ -494,10 +481,6 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
-    if (const char *env = getenv("MP_WPC")) h->use_wpc = atoi(env) != 0;
-    if (const char *env = getenv("MP_WPC_NEAR_LOG2")) { const int v = atoi(env); if (v <= -2 && v >= -26) h->wpc_near = ldexpf(1.f, v); }
-    if (const char *env = getenv("MP_WPC_BCAP_LOG2")) { const int v = atoi(env); if (v <= 0 && v >= -26) h->wpc_bcap = ldexpf(1.f, v); }
-    if (const char *env = getenv("MP_WPC_WINDOW")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16) h->wpc_window = v; }
     if (const char *env = getenv("MP_BLK_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->blk_tpt = v; }
     if (const char *env = getenv("MP_BLK_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) h->blk_cs = v; }
     h->sm_count = prop.multiProcessorCount;
@@ -527,7 +510,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
-        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_scan, N * sizeof(int) }, { (void **)&h->d_minv, N * sizeof(int) }, { (void **)&h->d_work, (MP_CNT_N + 16) * sizeof(unsigned long long) },   // + 16 profiling slots (MP_WPC_PROFILE builds)
+        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_scan, N * sizeof(int) }, { (void **)&h->d_minv, N * sizeof(int) }, { (void **)&h->d_work, MP_CNT_N * sizeof(unsigned long long) },
         { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) }, { (void **)&h->d_mlow, C * ((N + 31) / 32) * sizeof(float) },
     };
     for (auto &r : reqs) {
@@ -1327,16 +1310,7 @@ int mp_get_work_counters(mp_engine *h, uint64_t *out, int reset)
     CK(cudaMemcpyAsync(dev, h->d_work, sizeof(dev), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < MP_CNT_N; i++) out[i] = (uint64_t)dev[i];
-    if (reset) CK(cudaMemsetAsync(h->d_work, 0, (MP_CNT_N + 16) * sizeof(unsigned long long), h->stream));
-    return MP_OK;
-}
-// profiling slots behind the work counters (filled by builds with -DMP_WPC_PROFILE only; reset with the work counters)
-int mp_debug_counters(mp_engine *h, uint64_t *out16)
-{
-    if (!h || !out16) return MP_ERR_ARG;
-    CK(cudaSetDevice(h->cfg.device));
-    CK(cudaMemcpyAsync(out16, h->d_work + MP_CNT_N, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (reset) CK(cudaMemsetAsync(h->d_work, 0, sizeof(dev), h->stream));
     return MP_OK;
 }
 int mp_probe_peaks(mp_engine *h, double *out4)

@@ -81,9 +81,6 @@ struct mp_engine {
     std::vector<uint32_t> morton;     // Morton code of every patch
     std::vector<int> blk_of, scan_host;   // block of every patch; visiting order of the scan (position -> patch)
     int blk_tpt = 0, blk_cs = 0;      // threads per block task / cluster size (0 = choose); MP_BLK_TPT, MP_BLK_CS override
-    float wpc_bcap = 0.03125f;        // a group whose remainder bound exceeds this (log2 units) is evaluated in the first pass (MP_WPC_BCAP_LOG2)
-    float wpc_near = 0.015625f;       // NEAR threshold of the windowed scan (2^-6; MP_WPC_NEAR_LOG2 overrides)
-    int use_wpc = 1, wpc_window = 4;  // windowed one-CTA scan where a task's targets fit one CTA's shared memory (MP_WPC=0 disables; MP_WPC_WINDOW = 4 | 8 | 16)
     std::vector<int> blk_slot_lo, blk_slot_hi, blk_tl_off, blk_tl_n;   // per block: own scan-order slots, target list
     std::vector<int> colour_off, colour_n;     // per colour: first block task and count in d_btasks
     int blk_nl_max = 0;               // largest target list
@@ -174,9 +171,5 @@ int mp_launch_sweep_fast_dense(mp_engine *h, int cs, int tpt);
 // culled scan: nclusters whole (chain, year) tasks (btasks == nullptr) or block tasks (mp::BlockTask array on the device)
 int mp_launch_sweep_cull_linear(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks);
 int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks);
-// windowed one-CTA scan (mp_sweep_wpc.cuh): nclusters whole tasks or block tasks of at most nl_max targets; window = candidates in flight
-int mp_launch_sweep_wpc_linear(mp_engine *h, int window, int nl_max, int nclusters, const void *btasks);
-int mp_launch_sweep_wpc_coords(mp_engine *h, int window, int nl_max, int nclusters, const void *btasks);
-size_t mp_wpc_smem_bytes(int nl_max);
 // tensor-core connectivity of every chain with one (alpha, b) (mp_conn_gemm.cu)
 int mp_launch_conn_gemm(mp_engine *h, double alpha);

@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "mp_get_timing", "mp_probe_peaks", "mp_get_stream", "mp_exact_posterior", "mp_exact_last_error", "mp_simulate_ensemble", "mp_exact_variant", "mp_set_shard", "mp_sweep_phase",
     "mp_get_scan_order", "mp_get_work_counters", "mp_get_scan_geometry", "mp_get_conn_path", "mp_set_scan_blocks",
     "mp_comm_unique_id", "mp_comm_init", "mp_comm_init_all", "mp_comm_destroy", "mp_comm_rank", "mp_comm_size", "mp_comm_last_error",
-    "mp_gather_draws", "mp_gather_draws_all", "mp_debug_counters", "mp_sweep_sharded", "mp_sweep_sharded_all",
+    "mp_gather_draws", "mp_gather_draws_all", "mp_sweep_sharded", "mp_sweep_sharded_all",
 )
 
 
@@ -134,7 +134,6 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
     L.mp_probe_peaks.argtypes = [vp, dp]
     L.mp_get_work_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
-    L.mp_debug_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mp_get_scan_geometry.argtypes = [vp, C.POINTER(C.c_int)]
     L.mp_get_conn_path.argtypes = [vp]
     L.mp_exact_posterior.argtypes = [C.c_int, i8p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
@@ -472,11 +471,6 @@ class Engine:
         out = (C.c_uint64 * len(WORK_COUNTERS))()
         self._ck(self.lib.mp_get_work_counters(self.h, out, int(reset)), "mp_get_work_counters")
         return dict(zip(WORK_COUNTERS, [int(v) for v in out]))
-
-    def debug_counters(self):
-        out = (C.c_uint64 * 16)()
-        self._ck(self.lib.mp_debug_counters(self.h, out), "mp_debug_counters")
-        return [int(v) for v in out]
 
     def conn_path(self):
         """Kernel that evaluated the connectivity last: "k_conn" or "gemm" (tcgen05 contraction for chains sharing alpha, b)."""
