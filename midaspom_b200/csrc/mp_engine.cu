@@ -1189,19 +1189,29 @@ int mp_get_draws(mp_engine *h, int first, int count, double *out)
 
 // ---- forward simulator
 extern "C++" template <typename R> int simulate_t(mp_engine *h, const mp_params *d_pars, int per_sim, const uint8_t *d_z0, int nyears,
-                                                  int nsims, uint64_t seed, int era_all, uint8_t *d_zout, int32_t *d_occ, uint8_t *d_work)
+                                                  int nsims, uint64_t seed, int era_all, uint8_t *d_zout, int32_t *d_occ, uint8_t *d_zc,
+                                                  uint8_t *d_yc, int *d_list, int *d_nlist, R *d_aw)
 {
     Timed tm(h, MP_K_SIM);
-    const double *area = h->have_area ? h->d_area : nullptr;
-    const int nthr = (int)std::min<size_t>(256, ((nN(h) + 31) / 32) * 32);
-#define SIM(G) k_simulate<R, G><<<nsims, nthr, 0, h->stream>>>(view<R>(h), d_pars, per_sim, area, d_z0, nyears, seed, 0u, era_all, d_zout, d_occ, d_work)
-    switch (h->geom) {
-    case MP_GEOM_LINEAR: SIM(MP_GEOM_LINEAR); break;
-    case MP_GEOM_COORDS: SIM(MP_GEOM_COORDS); break;
-    default: SIM(MP_GEOM_DENSE); break;
-    }
-#undef SIM
+    const int n = h->cfg.n_patches, npar = per_sim ? nsims : 1;
+    k_area_weights<R><<<dim3((n + 255) / 256, npar), 256, 0, h->stream>>>(d_pars, h->have_area ? h->d_area : nullptr, d_aw, n);
     CK(cudaGetLastError());
+    if (d_occ) CK(cudaMemsetAsync(d_occ, 0, (size_t)nsims * (nyears + 1) * 4, h->stream));
+    k_sim_init<<<nsims, 256, 0, h->stream>>>(d_z0, per_sim, n, nyears, d_zc, d_zout, d_occ);
+    CK(cudaGetLastError());
+    const dim3 cgrid((n + 127) / 128, nsims);
+    for (int t = 0; t < nyears; t++) {
+        k_sim_ext<R><<<nsims, 1024, 0, h->stream>>>(d_pars, per_sim, n, seed, 0u, t, era_all, d_zc, d_yc, d_list, d_nlist);
+        CK(cudaGetLastError());
+#define SIM(G) k_sim_col<R, G><<<cgrid, 128, 0, h->stream>>>(view<R>(h), d_pars, per_sim, d_aw, d_yc, d_list, d_nlist, seed, 0u, t, nyears, era_all, d_zc, d_zout, d_occ)
+        switch (h->geom) {
+        case MP_GEOM_LINEAR: SIM(MP_GEOM_LINEAR); break;
+        case MP_GEOM_COORDS: SIM(MP_GEOM_COORDS); break;
+        default: SIM(MP_GEOM_DENSE); break;
+        }
+#undef SIM
+        CK(cudaGetLastError());
+    }
     return MP_OK;
 }
 static int simulate_impl(mp_engine *h, const mp_params *par, int per_sim, const uint8_t *z0, int nyears, int nsims, uint64_t seed,
@@ -1214,28 +1224,34 @@ static int simulate_impl(mp_engine *h, const mp_params *par, int per_sim, const 
     const int npar = per_sim ? nsims : 1;
     for (int i = 0; i < npar; i++) REQUIRE(par[i].K > 0.0 && par[i].alpha > 0.0, MP_ERR_ARG, "mp_simulate: need K>0 and alpha>0");
     const size_t N = nN(h), nz0 = per_sim ? (size_t)nsims * N : N;
-    uint8_t *d_z0 = nullptr, *d_zout = nullptr, *d_work = nullptr;
-    int32_t *d_occ = nullptr;
-    mp_params *d_pars = nullptr;
+    // one arena per call: start states, parameters, current / intermediate state, survivor lists, A^b, outputs
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_z0 = carve(nz0), o_par = carve((size_t)npar * sizeof(mp_params)), o_zc = carve((size_t)nsims * N), o_yc = carve((size_t)nsims * N),
+                 o_list = carve((size_t)nsims * N * 4), o_nl = carve((size_t)nsims * 4), o_aw = carve((size_t)npar * N * 8),
+                 o_zout = carve(z_out ? (size_t)nsims * (nyears + 1) * N : 0), o_occ = carve(occupied_out ? (size_t)nsims * (nyears + 1) * 4 : 0);
+    unsigned char *arena = nullptr;
     int rc = MP_OK;
     cudaError_t e;
 #define SIMCK(call) if ((e = (call)) != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e); rc = MP_ERR_CUDA; goto done; }
-    SIMCK(cudaMalloc(&d_z0, nz0));
-    SIMCK(cudaMalloc(&d_pars, (size_t)npar * sizeof(mp_params)));
-    SIMCK(cudaMalloc(&d_work, (size_t)nsims * 2 * N));
-    if (z_out) SIMCK(cudaMalloc(&d_zout, (size_t)nsims * (nyears + 1) * N));
-    if (occupied_out) SIMCK(cudaMalloc(&d_occ, (size_t)nsims * (nyears + 1) * 4));
-    SIMCK(cudaMemcpyAsync(d_z0, z0, nz0, cudaMemcpyHostToDevice, h->stream));
-    SIMCK(cudaMemcpyAsync(d_pars, par, (size_t)npar * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
-    rc = is64(h) ? simulate_t<double>(h, d_pars, per_sim, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work)
-                 : simulate_t<float>(h, d_pars, per_sim, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_work);
-    if (rc != MP_OK) goto done;
-    if (z_out) SIMCK(cudaMemcpyAsync(z_out, d_zout, (size_t)nsims * (nyears + 1) * N, cudaMemcpyDeviceToHost, h->stream));
-    if (occupied_out) SIMCK(cudaMemcpyAsync(occupied_out, d_occ, (size_t)nsims * (nyears + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-    SIMCK(cudaStreamSynchronize(h->stream));
+    SIMCK(cudaMalloc(&arena, std::max<size_t>(off, 256)));
+    {
+        uint8_t *d_z0 = arena + o_z0, *d_zc = arena + o_zc, *d_yc = arena + o_yc, *d_zout = z_out ? arena + o_zout : nullptr;
+        mp_params *d_pars = (mp_params *)(arena + o_par);
+        int *d_list = (int *)(arena + o_list), *d_nlist = (int *)(arena + o_nl);
+        int32_t *d_occ = occupied_out ? (int32_t *)(arena + o_occ) : nullptr;
+        SIMCK(cudaMemcpyAsync(d_z0, z0, nz0, cudaMemcpyHostToDevice, h->stream));
+        SIMCK(cudaMemcpyAsync(d_pars, par, (size_t)npar * sizeof(mp_params), cudaMemcpyHostToDevice, h->stream));
+        rc = is64(h) ? simulate_t<double>(h, d_pars, per_sim, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_zc, d_yc, d_list, d_nlist, (double *)(arena + o_aw))
+                     : simulate_t<float>(h, d_pars, per_sim, d_z0, nyears, nsims, seed, era_all, d_zout, d_occ, d_zc, d_yc, d_list, d_nlist, (float *)(arena + o_aw));
+        if (rc != MP_OK) goto done;
+        if (z_out) SIMCK(cudaMemcpyAsync(z_out, d_zout, (size_t)nsims * (nyears + 1) * N, cudaMemcpyDeviceToHost, h->stream));
+        if (occupied_out) SIMCK(cudaMemcpyAsync(occupied_out, d_occ, (size_t)nsims * (nyears + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+        SIMCK(cudaStreamSynchronize(h->stream));
+    }
 #undef SIMCK
 done:
-    cudaFree(d_z0); cudaFree(d_pars); cudaFree(d_work); cudaFree(d_zout); cudaFree(d_occ);
+    cudaFree(arena);
     return rc;
 }
 int mp_simulate(mp_engine *h, const mp_params *par, const uint8_t *z0, int nyears, int nsims, uint64_t seed, int era_all,

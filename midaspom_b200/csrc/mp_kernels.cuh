@@ -8,7 +8,7 @@
 //  k_sweep_y       Gibbs scan of y_t | z with rank-1 updates of S_t in shared memory
 //  k_update_z      Gibbs update of latent occupancy cells (conditionally independent given y)
 //  k_propose_* / k_decide_* / k_update_ep / k_record   Metropolis bookkeeping, one warp per chain
-//  k_simulate      forward simulator (future.c:64-110)
+//  k_sim_init / k_sim_ext / k_sim_col   forward simulator (future.c:64-110)
 #pragma once
 #include "mp_device.cuh"
 #include "mp_conn.cuh"   // k_pack_sources, k_group_min_S, k_conn
@@ -534,56 +534,103 @@ k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__res
 }
 
 // ------------------------------------------------------------------ forward simulator
-// One CTA per simulated trajectory (future.c:359-386 loops over simulations; simpij :64-110 is one
-// year).  survive iff u > E (:78); colonise iff u < C (:100).
-template <typename R, int GEOM>
-__global__ void k_simulate(Landscape<R> ls, const mp_params *__restrict__ pars, int per_sim, const double *__restrict__ area,
-                           const uint8_t *__restrict__ z0_all, int nyears, uint64_t seed, uint32_t sim0, int era_all,
-                           uint8_t *__restrict__ z_out, int32_t *__restrict__ occ_out, uint8_t *__restrict__ work)
+// Forward simulator (future.c:359-386 loops over simulations; simpij :64-110 is one year): survive iff u > E (:78),
+// colonise iff u < C (:100).  One year = two launches over all trajectories:
+//   k_sim_ext   one CTA per trajectory: extinction draws and the ORDERED list of the surviving sources (ascending patch
+//               number, the order in which simpij and the CPU twin accumulate S)
+//   k_sim_col   grid (target tiles, trajectories): S of 128 targets from the survivor list staged through shared memory
+//               (coordinates and A_l^b, precomputed once per parameter set by k_area_weights), then the colonisation draws
+// so a single large landscape spreads over the whole GPU (synth.make_workload_large generates cfg5 with it).
+static __global__ void __launch_bounds__(256)
+k_sim_init(const uint8_t *__restrict__ z0_all, int per_sim, int n, int nyears, uint8_t *__restrict__ zc, uint8_t *__restrict__ z_out,
+           int32_t *__restrict__ occ_out)
 {
     __shared__ double scratch[32];
-    const int n = ls.n, tid = threadIdx.x, nthr = blockDim.x;
-    const uint32_t sim = sim0 + blockIdx.x;
-    const mp_params p = pars[per_sim ? blockIdx.x : 0];                  // per-trajectory parameters and start (future.c:359-381)
     const uint8_t *z0 = z0_all + (per_sim ? (size_t)blockIdx.x * n : 0);
-    uint8_t *zc = work + (size_t)blockIdx.x * 2 * n, *yc = zc + n;     // current state, intermediate state
-    const Trans<R> tr = make_trans<R>(p, era_all);
     int cnt = 0;
-    for (int k = tid; k < n; k += nthr) { zc[k] = z0[k] != 0; cnt += zc[k];
-                                           if (z_out) z_out[(size_t)blockIdx.x * (nyears + 1) * n + k] = zc[k]; }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const uint8_t v = z0[k] != 0;
+        zc[(size_t)blockIdx.x * n + k] = v; cnt += v;
+        if (z_out) z_out[(size_t)blockIdx.x * (nyears + 1) * n + k] = v;
+    }
     cnt = (int)(block_sum((double)cnt, scratch) + 0.5);
-    if (tid == 0 && occ_out) occ_out[(size_t)blockIdx.x * (nyears + 1)] = cnt;
+    if (threadIdx.x == 0 && occ_out) occ_out[(size_t)blockIdx.x * (nyears + 1)] = cnt;
+}
+template <typename R>
+__global__ void __launch_bounds__(1024)
+k_sim_ext(const mp_params *__restrict__ pars, int per_sim, int n, uint64_t seed, uint32_t sim0, int t, int era_all,
+          const uint8_t *__restrict__ zc, uint8_t *__restrict__ yc, int *__restrict__ list, int *__restrict__ nlist)
+{
+    __shared__ int s_cnt[1024];
+    const int tid = threadIdx.x;
+    const uint32_t sim = sim0 + blockIdx.x;
+    const Trans<R> tr = make_trans<R>(pars[per_sim ? blockIdx.x : 0], era_all);
+    const uint8_t *z = zc + (size_t)blockIdx.x * n;
+    uint8_t *y = yc + (size_t)blockIdx.x * n;
+    const int per = (n + 1023) / 1024, k0 = min(n, tid * per), k1 = min(n, k0 + per);
+    int cnt = 0;
+    for (int k = k0; k < k1; k++) {
+        const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_EXT, (uint32_t)k, 0);
+        const uint8_t v = z[k] && (u01(r.x) > (double)tr.E);
+        y[k] = v; cnt += v;
+    }
+    s_cnt[tid] = cnt;
     __syncthreads();
-    for (int t = 0; t < nyears; t++) {
-        for (int k = tid; k < n; k += nthr) {
-            const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_EXT, (uint32_t)k, 0);
-            yc[k] = zc[k] && (u01(r.x) > (double)tr.E);
-        }
+    for (int o = 1; o < 1024; o <<= 1) {                  // inclusive Hillis-Steele scan
+        const int v = tid >= o ? s_cnt[tid - o] : 0;
         __syncthreads();
-        int c2 = 0;
-        for (int k = tid; k < n; k += nthr) {
-            R kx = 0, ky = 0;
-            if (GEOM == MP_GEOM_COORDS) { kx = ls.px[k]; ky = ls.py[k]; }
-            double s = 0.0;
-            for (int l = 0; l < n; l++) {
-                if (l == k || !yc[l]) continue;
-                R lx = 0, ly = 0;
-                if (GEOM == MP_GEOM_COORDS) { lx = ls.px[l]; ly = ls.py[l]; }
-                const R awl = area_pre<R>((area && p.b != 0.0) ? pow(area[l], p.b) : 1.0);
-                s += (double)pair_weight<R, GEOM>(ls, alpha_pre<R>(p.alpha), awl, k, l, kx, ky, lx, ly);
-            }
-            const R C = col_prob<R>(tr, (R)s, source_term<R>(ls, tr, k));
-            const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_COL, (uint32_t)k, 0);
-            const uint8_t v = yc[k] ? 1 : (u01(r.x) < (double)C);
-            c2 += v;
-            if (z_out) z_out[((size_t)blockIdx.x * (nyears + 1) + t + 1) * n + k] = v;
-            // zc is only read through yc in this phase, so it can be overwritten in place
-            zc[k] = v;
-        }
-        c2 = (int)(block_sum((double)c2, scratch) + 0.5);
-        if (tid == 0 && occ_out) occ_out[(size_t)blockIdx.x * (nyears + 1) + t + 1] = c2;
+        s_cnt[tid] += v;
         __syncthreads();
     }
+    int off = s_cnt[tid] - cnt;
+    int *out = list + (size_t)blockIdx.x * n;
+    for (int k = k0; k < k1; k++) if (y[k]) out[off++] = k;
+    if (tid == 1023) nlist[blockIdx.x] = s_cnt[1023];
+}
+template <typename R, int GEOM>
+__global__ void __launch_bounds__(128)
+k_sim_col(Landscape<R> ls, const mp_params *__restrict__ pars, int per_sim, const R *__restrict__ aw /* [parameter set][n] */,
+          const uint8_t *__restrict__ yc, const int *__restrict__ list, const int *__restrict__ nlist, uint64_t seed, uint32_t sim0,
+          int t, int nyears, int era_all, uint8_t *__restrict__ zc, uint8_t *__restrict__ z_out, int32_t *__restrict__ occ_out)
+{
+    __shared__ int s_l[128];
+    __shared__ R s_x[128], s_y[128], s_a[128];
+    const int n = ls.n, tid = threadIdx.x, k = blockIdx.x * 128 + tid, si = blockIdx.y;
+    const uint32_t sim = sim0 + si;
+    const mp_params p = pars[per_sim ? si : 0];
+    const Trans<R> tr = make_trans<R>(p, era_all);
+    const R apre = alpha_pre<R>(p.alpha);
+    const R *awp = aw + (per_sim ? (size_t)si * n : 0);
+    const int *src = list + (size_t)si * n, ns = nlist[si];
+    const int kq = min(k, n - 1);
+    R kx = 0, ky = 0;
+    if (GEOM == MP_GEOM_COORDS) { kx = ls.px[kq]; ky = ls.py[kq]; }
+    double s = 0.0;
+    for (int j0 = 0; j0 < ns; j0 += 128) {
+        __syncthreads();
+        if (j0 + tid < ns) {
+            const int l = src[j0 + tid];
+            s_l[tid] = l; s_a[tid] = awp[l];
+            if (GEOM == MP_GEOM_COORDS) { s_x[tid] = ls.px[l]; s_y[tid] = ls.py[l]; }
+        }
+        __syncthreads();
+        const int m = min(128, ns - j0);
+        for (int j = 0; j < m; j++) {                     // ascending l: the accumulation order of simpij / the CPU twin
+            const int l = s_l[j];
+            if (l == kq) continue;
+            s += (double)pair_weight<R, GEOM>(ls, apre, s_a[j], kq, l, kx, ky, GEOM == MP_GEOM_COORDS ? s_x[j] : (R)0, GEOM == MP_GEOM_COORDS ? s_y[j] : (R)0);
+        }
+    }
+    int v = 0;
+    if (k < n) {
+        const R C = col_prob<R>(tr, (R)s, source_term<R>(ls, tr, k));
+        const uint4 r = rng(seed, sim, (uint32_t)t, RK_SIM_COL, (uint32_t)k, 0);
+        v = yc[(size_t)si * n + k] ? 1 : (u01(r.x) < (double)C);
+        zc[(size_t)si * n + k] = (uint8_t)v;              // zc is only read through yc in this launch
+        if (z_out) z_out[((size_t)si * (nyears + 1) + t + 1) * n + k] = (uint8_t)v;
+    }
+    const int c2 = __reduce_add_sync(0xffffffffu, v);
+    if ((tid & 31) == 0 && occ_out && c2) atomicAdd(&occ_out[(size_t)si * (nyears + 1) + t + 1], c2);
 }
 
 // ------------------------------------------------------------------ peak probes (roofline denominators)

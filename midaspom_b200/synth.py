@@ -42,9 +42,9 @@ def kernel_matrix(px, py, area, alpha, b, dtype=np.float32):
 
 
 def make_workload_large(name: str, seed: int = 12345, device: int = 0):
-    """Same generative model for landscapes whose N x N kernel matrix does not fit the host (cfg5):
-    the connectivity of each simulated year comes from the engine itself (mp_connectivity on a two-row
-    engine), the Bernoulli draws stay in numpy.  Needs a GPU."""
+    """Same generative model for landscapes whose N x N kernel matrix does not fit the host (cfg5): the occupancy history
+    comes from the engine's own forward simulator (mp_simulate: simpij, main_MIDASPOM_future.c:64-110, with Philox draws),
+    after one mp_connectivity call that normalises c like make_workload does.  Needs a GPU."""
     from .engine import Engine, FP32
     w = WORKLOADS[name]
     n, T = w["n"], w["T"]
@@ -57,17 +57,14 @@ def make_workload_large(name: str, seed: int = 12345, device: int = 0):
     eng.set_landscape_coords(px, py, area)
     eng.set_source_units(None)
     eng.set_params([dict(e=e, c=1.0, alpha=alpha, b=b)])
-    z = np.zeros((T, n), dtype=np.uint8)
-    z[0] = rng.random(n) < 0.5
-    c = None
-    for t in range(T - 1):
-        y = z[t] & (rng.random(n) > e)
-        eng.set_state(np.stack([z[t], z[t]])[None], y[None, None])
-        S = eng.connectivity()[0, 0]
-        if c is None:
-            c = float(TRUTH["target_mean_C"] / max(S.mean(), 1e-30))
-        z[t + 1] = np.where(y == 1, 1, rng.random(n) < np.minimum(1.0, c * S))
+    z0 = (rng.random(n) < 0.5).astype(np.uint8)
+    y0 = z0 & (rng.random(n) > e)
+    eng.set_state(np.stack([z0, z0])[None], y0[None, None])
+    S0 = eng.connectivity()[0, 0]
+    c = float(TRUTH["target_mean_C"] / max(S0.mean(), 1e-30))      # mean colonisation probability of the first transition ~0.3
+    zs, _ = eng.simulate(dict(e=e, c=c, alpha=alpha, b=b), z0, T - 1, nsims=1, seed=seed)
     eng.close()
+    z = np.ascontiguousarray(zs[0], dtype=np.uint8)
     obs = z.astype(np.int8)
     hide = rng.random(z.shape) < 0.05
     hide[0] = False

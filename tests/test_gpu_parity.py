@@ -590,10 +590,10 @@ def test_fp32_culled_engine_posterior_matches_fp64_engine():
 
 
 # ------------------------------------------------------------------ forward simulator (a9)
-@pytest.mark.parametrize("geom", [O.GEOM_LINEAR, O.GEOM_COORDS])
-def test_simulator_follows_the_cpu_twin(geom):
+@pytest.mark.parametrize("geom,n,years,nsims", [(O.GEOM_LINEAR, 50, 12, 6), (O.GEOM_COORDS, 50, 12, 6), (O.GEOM_DENSE, 90, 5, 3),
+                                                (O.GEOM_COORDS, 700, 4, 3)])     # 700: several target tiles and survivor-list tiles
+def test_simulator_follows_the_cpu_twin(geom, n, years, nsims):
     rng = np.random.default_rng(21)
-    n, years, nsims = 50, 12, 6
     spec, z, _ = random_landscape(rng, n, 2, geom, areas=True)
     par = pdict(e=0.5, c=0.05, alpha=1 / 500, b=0.4, K=1.5, Ksrc=0.7, dsrc=60.0)
     spec_o = dict(spec); spec_o["era"] = np.ones(years, dtype=np.uint8)
