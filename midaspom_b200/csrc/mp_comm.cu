@@ -35,9 +35,12 @@ NcclApi g_nccl;
 bool load_nccl()
 {
     if (g_nccl.lib) return true;
-    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    // MP_NCCL_LIB names the copy to use.  A process that will also load PyTorch must take PyTorch's bundled NCCL: two libraries
+    // with the SONAME libnccl.so.2 cannot coexist, and libtorch_cuda.so needs symbols of its own (newer) version -- the Python
+    // mirror sets the variable to that copy before the first mp_comm_* call (engine.py: _prefer_bundled_nccl).
+    const char *names[] = { getenv("MP_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
     void *lib = nullptr;
-    for (const char *nm : names) if ((lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    for (const char *nm : names) if (nm && *nm && (lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
     if (!lib) { g_nccl.err = std::string("libnccl.so.2 not found: ") + dlerror(); return false; }
     bool ok = true;
     auto sym = [&](const char *nm) { void *p = dlsym(lib, nm); if (!p) { ok = false; g_nccl.err = std::string("NCCL symbol missing: ") + nm; } return p; };

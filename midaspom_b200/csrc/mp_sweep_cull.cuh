@@ -176,7 +176,13 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             if (4 * q + 2 < SP) v[(4 * q + 2) % SP] = warp_sum_f(t.z);
             if (4 * q + 3 < SP) v[(4 * q + 3) % SP] = warp_sum_f(t.w);
         };
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // value of a slot of the exchange buffer, zero for lanes without a sender (a plain predicated LDS: selecting between
+        // a reference into shared memory and a local constant made the compiler emit a generic load from the stack per trip)
+        auto slot_of = [&](const float4 *base, int nslot, int q) -> float4 {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < nslot) t = base[lane * NV + q];
+            return t;
+        };
 #pragma unroll
         for (int c = 0; c < SP; c++) v[c] = warp_sum_f(v[c]);
         if (HIER) {
@@ -186,7 +192,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < NV; q++) unpack_sum(q, lane < NW ? wred[round][p][lane][q] : zero4);
+            for (int q = 0; q < NV; q++) unpack_sum(q, slot_of(&wred[round][p][0][0], NW, q));
         }
         if (CS > 1) {
             const uint32_t boff = (uint32_t)(round * 2 + p) * 8u;
@@ -199,7 +205,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             }
             mbar_wait(bar_local + boff, (u >> 1) & 1u);
 #pragma unroll
-            for (int q = 0; q < NV; q++) unpack_sum(q, lane < NSLOT ? red[round][p][lane][q] : zero4);
+            for (int q = 0; q < NV; q++) unpack_sum(q, slot_of(&red[round][p][0][0], NSLOT, q));
             return;
         }
         if (HIER) return;
@@ -209,7 +215,7 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < NV; q++) unpack_sum(q, lane < NSLOT ? red[round][p][lane][q] : zero4);
+        for (int q = 0; q < NV; q++) unpack_sum(q, slot_of(&red[round][p][0][0], NSLOT, q));
     };
     // weight of (candidate k, target in slot data tq)
     auto weight = [&](const float4 &tq, int k, float kx, float ky, float lawk) -> float {

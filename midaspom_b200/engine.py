@@ -219,8 +219,24 @@ class Engine:
     COMM_ID_BYTES = 128
 
     @staticmethod
+    def _prefer_bundled_nccl():
+        """Point the library at the NCCL that PyTorch bundles (MP_NCCL_LIB) unless the caller chose one: the process may
+        import torch later, and two different libnccl.so.2 cannot live in one process."""
+        import importlib.util
+        import os
+        if os.environ.get("MP_NCCL_LIB"):
+            return
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+            cand = Path(root) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                os.environ["MP_NCCL_LIB"] = str(cand)
+                return
+
+    @staticmethod
     def comm_unique_id() -> bytes:
         """mp_comm_unique_id: the 128 bytes rank 0 hands to every rank of a communicator."""
+        Engine._prefer_bundled_nccl()
         buf = C.create_string_buffer(Engine.COMM_ID_BYTES)
         rc = load_library().mp_comm_unique_id(buf)
         if rc != 0:
@@ -228,12 +244,14 @@ class Engine:
         return buf.raw
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        Engine._prefer_bundled_nccl()
         buf = C.create_string_buffer(bytes(unique_id), Engine.COMM_ID_BYTES)
         self._ck(self.lib.mp_comm_init(self.h, int(nranks), int(rank), buf), "mp_comm_init")
 
     @staticmethod
     def comm_init_all(engines):
         """One process driving one engine per device: a communicator over all of them (mp_comm_init_all)."""
+        Engine._prefer_bundled_nccl()
         arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
         engines[0]._ck(engines[0].lib.mp_comm_init_all(arr, len(engines)), "mp_comm_init_all")
 

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Turn an .ncu-rep (read with `ncu -i`) into the small tracked summaries under profiles/:
-   python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_ncu_full  [note]"""
+   python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r02_ncu_scan  [note] [workload tag, e.g. cfg3]"""
 import csv, json, subprocess, sys, io
 
 rep, out = sys.argv[1], sys.argv[2]
 note = sys.argv[3] if len(sys.argv) > 3 else ""
+workload = sys.argv[4] if len(sys.argv) > 4 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -16,12 +17,13 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "sm__cycles_active.avg", "sm__cycles_elapsed.max"]
+        "sm__cycles_active.avg", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 summ = []
 md = [f"# ncu --set full summary ({rep.split('/')[-1]})", "", note, ""]
 for r in rows[2:]:
     name = r[idx["Kernel Name"]]
-    d = {"kernel": name}
+    d = {"kernel": name, "workload": workload}
     md += [f"## `{name[:90]}`", "", "| metric | value | unit |", "|---|---|---|"]
     for w in WANT:
         if w in idx:

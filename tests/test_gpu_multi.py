@@ -99,3 +99,23 @@ def test_gather_draws_over_two_processes():
     solo.sweep(nsw)
     assert (solo.get_draws() == res[0][1]).all()
     solo.close()
+
+
+@pytest.mark.skipif(ngpu() < 2, reason="needs 2 GPUs")
+def test_driver_G_flag_writes_the_draws_of_a_single_gpu_run(tmp_path):
+    """driver/midaspom -G 0,1 (the drop-in for `mpirun -np 2 MIDASPOM_MPI.out`, run_examples_MPI.sh:8): chains split over two
+    devices, draws gathered by NCCL inside the library (mp_comm_init_all + mp_gather_draws_all).  Philox streams are keyed by
+    the global chain id, so the draw file equals that of the same chains on one GPU, line for line."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    subprocess.run(["make", "-C", str(root / "driver")], check=True, capture_output=True)
+    example = root / "tests" / "golden" / "occupancies_example.txt"
+    outs = []
+    for tag, dev in (("one", ["-g", "0"]), ("two", ["-G", "0,1"])):
+        res = subprocess.run([str(root / "driver" / "midaspom"), "-m", "400", "-d", "100", "-s", "21", "-n", "600", "-c", "8", "-i", str(example),
+                              "-o", str(tmp_path / f"p_{tag}.txt"), "-t", str(tmp_path / f"d_{tag}.txt")] + dev, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        outs.append(((tmp_path / f"d_{tag}.txt").read_text(), (tmp_path / f"p_{tag}.txt").read_text(), res.stdout))
+    assert "on 2 GPUs" in outs[1][2]
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
