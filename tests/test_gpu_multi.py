@@ -56,6 +56,38 @@ def test_sharded_sweep_over_two_gpus_in_one_process_equals_single_engine(n):
         e.close()
 
 
+@pytest.mark.skipif(ngpu() < 2, reason="needs 2 GPUs")
+def test_sharded_sweep_with_scan_blocks_over_two_gpus_equals_single_engine():
+    """The same with the block grid of the scan on (21,025 patches, 4 x 4 cells, 9 colours): every rank scans the blocks of its
+    years concurrently; the per-year block decisions depend on the year's own data, so nothing changes bit for bit."""
+    from test_gpu_blocks import ALPHA, auto_grid, wide_landscape
+    rng = np.random.default_rng(33)
+    T, C, nsw = 5, 1, 3
+    spec, z, y = wide_landscape(rng, 145, T)
+    par = pdict(e=0.4, c=0.05, alpha=ALPHA, b=0.5)
+    kw = dict(sample_alpha=1, sample_b=1, c_max=0.5, alpha_min=1e-3, alpha_max=1e-1, n_adapt=4)
+    grid = auto_grid(spec, z, y, par, 3)
+    assert grid[0] * grid[1] >= 16
+    ref = fresh_engine(spec, 0, C, nsw, par, kw, blocks=grid)
+    ref.work_counters(reset=True)
+    ref.sweep(nsw)
+    assert ref.work_counters()["scan_blocks"] > 0
+    want = (ref.get_draws(), ref.get_state(), ref.get_connectivity())
+    ref.close()
+    engs = [fresh_engine(spec, d, C, nsw, par, kw, blocks=grid) for d in range(2)]
+    mb.Engine.comm_init_all(engs)
+    mb.Engine.sweep_sharded_all(engs, nsw)
+    for e in engs:
+        e.synchronize()
+        assert e.work_counters()["scan_blocks"] > 0
+        got = (e.get_draws(), e.get_state(), e.get_connectivity())
+        assert (got[0] == want[0]).all()
+        assert (got[1][0] == want[1][0]).all() and (got[1][1] == want[1][1]).all()
+        assert (got[2] == want[2]).all()
+    for e in engs:
+        e.close()
+
+
 def _rank_main(rank, world, uid_q, out_q, spec, nsw):
     import midaspom_b200 as mb2
     if rank == 0:

@@ -84,3 +84,25 @@ def test_scan_order_is_the_morton_curve_of_planar_coordinates():
     step = np.hypot(np.diff(px[order]), np.diff(py[order]))
     assert np.median(step) < 0.15 * np.median(np.hypot(px - px[::-1], py - py[::-1]))
     assert O.scan_order(O.Model(obs, geom=O.GEOM_LINEAR, spacing=100.0)).tolist() == list(range(n))
+
+
+def test_scan_order_with_a_block_grid_visits_colour_by_colour():
+    """Block grid of the scan (spom_model.blk_nx, blk_ny, blk_k; engine: mp_set_scan_blocks): the order is a permutation that
+    visits the cells colour by colour (colour = (bx mod k) + k (by mod k)), cell by cell inside a colour, and in plain Morton
+    order inside a cell; a 1 x 1 grid is the plain Morton order."""
+    rng = np.random.default_rng(3)
+    n, nx, ny, k = 2000, 5, 4, 2
+    px, py = rng.uniform(0, 1000.0, n), rng.uniform(0, 800.0, n)
+    obs = np.zeros((2, n), dtype=np.int8)
+    plain = O.scan_order(O.Model(obs, geom=O.GEOM_COORDS, px=px, py=py))
+    assert (O.scan_order(O.Model(obs, geom=O.GEOM_COORDS, px=px, py=py, scan_blocks=(1, 1, 1))) == plain).all()
+    order = O.scan_order(O.Model(obs, geom=O.GEOM_COORDS, px=px, py=py, scan_blocks=(nx, ny, k)))
+    assert sorted(order.tolist()) == list(range(n))
+    bx = np.minimum(((px - px.min()) / ((px.max() - px.min()) / nx)).astype(int), nx - 1)
+    by = np.minimum(((py - py.min()) / ((py.max() - py.min()) / ny)).astype(int), ny - 1)
+    key = ((bx % k) + k * (by % k)) * (nx * ny) + by * nx + bx            # (colour, cell)
+    assert (np.diff(key[order]) >= 0).all()                                # colour-major, then cell
+    rank = np.empty(n, dtype=int); rank[plain] = np.arange(n)              # position in the plain Morton order
+    for g in np.unique(key):
+        inside = order[key[order] == g]
+        assert (np.diff(rank[inside]) > 0).all()                           # Morton order inside a cell
