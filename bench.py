@@ -255,7 +255,7 @@ def ncu_counters(workload, kernel):
                 pass
     c["source"] = src
     traffic = kd.get("dram_traffic_bytes_per_launch")
-    return c, (dict(bytes_per_launch=traffic, source=src) if traffic is not None else None)
+    return c, (dict(bytes_per_launch=traffic, source=src, note="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload") if traffic is not None else None)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -514,7 +514,7 @@ def roofline(workload, wl, cpg, ncand, kms, klaunch, work, geo, probe, hbm_peak,
     alg_bytes = cpg * (T - 1) * n * (8 + 1 + 1 + 1 + 8 + 1) + cpg * ncand * 32   # S,y,z_t,z_t+1 in; S,y out; candidate records
     frac = mufu_required / t_scan * 1e-9 / peak
     roof = dict(bound="sfu", kernel=kernel, achieved=mufu_required / t_scan * 1e-9, peak=peak, unit="Gop/s (MUFU)",
-                frac=frac, traffic=traffic, counters=counters,
+                frac=frac, traffic=(traffic or {}).get("bytes_per_launch"), traffic_detail=traffic, counters=counters,
                 share_of_step=kms["sweep_y"] / max(split_total_ms, 1e-9), ms_per_launch=t_scan * 1e3,
                 executed=dict(achieved=mufu_executed / t_scan * 1e-9, frac=mufu_executed / t_scan * 1e-9 / peak,
                               note="every MUFU the kernel issued for weights: speculative re-evaluations and the per-trip group bounds included "
@@ -540,7 +540,7 @@ def roofline(workload, wl, cpg, ncand, kms, klaunch, work, geo, probe, hbm_peak,
     roof["conn"] = dict(kernel="k_conn", ms_per_launch=t_conn * 1e3, achieved=conn_pairs * 2.0 / t_conn * 1e-9, unit="Gop/s (MUFU)",
                         frac=conn_pairs * 2.0 / t_conn * 1e-9 / peak, pairs_executed_per_launch=conn_pairs,
                         pairs_dense_per_launch=conn_total, share_of_step=kms["conn"] / max(split_total_ms, 1e-9),
-                        counters=c_counters, traffic=c_traffic)
+                        counters=c_counters, traffic=(c_traffic or {}).get("bytes_per_launch"), traffic_detail=c_traffic)
     return roof
 
 
