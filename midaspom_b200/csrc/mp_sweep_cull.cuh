@@ -290,8 +290,13 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
             const float sgn = cd.cur ? -1.f : 1.f;
             // groups where the weight exceeds 2^-36 min S: what is skipped stays far below the FP32 resolution of S even
             // when summed over every commit between two refreshes of S (at most 2^-36 x commits, in practice << 2^-30)
-            uint32_t m = __ballot_sync(0xffffffffu, lane < ept && !(wub < 1.4551915e-11f * Gw));
-            st_commit += __popc(m);
+            const bool reach = lane < ept && !(wub < 1.4551915e-11f * Gw);
+            // far part of the reach: every weight is below 2^-24 of the group's smallest S_hi, i.e. below half an ulp of each
+            // S_hi -- the two-sum would put all of it into S_lo and leave S_hi (and the group minimum) as they are, so only S_lo is
+            // touched.  |S_lo| stays below ~2^-13 S_hi between two normalising commits, far inside a float's exponent range of it.
+            const bool far = reach && wub < 5.9604645e-8f * Gw;
+            uint32_t m = __ballot_sync(0xffffffffu, reach && !far), mf = __ballot_sync(0xffffffffu, far);
+            st_commit += __popc(m) + __popc(mf);
             // B slots per trip: B independent (LDS, sqrt, ex2, two-sum, STS) chains, the loop is latency bound otherwise
             auto batch = [&](auto BB) {
                 constexpr int B = decltype(BB)::value;
@@ -324,6 +329,22 @@ k_sweep_y_cull(Landscape<float> ls, const int *__restrict__ perm, const mp_param
                 else if (left == 3) batch(std::integral_constant<int, 3>());
                 else if (left == 2) batch(std::integral_constant<int, 2>());
                 else batch(std::integral_constant<int, 1>());
+            }
+            auto batch_far = [&](auto BB) {
+                constexpr int B = decltype(BB)::value;
+                int jj[B];
+                float4 tq[B];
+#pragma unroll
+                for (int u = 0; u < B; u++) { jj[u] = __ffs((int)mf) - 1; mf &= mf - 1u; tq[u] = sT[tid + jj[u] * NT]; }
+#pragma unroll
+                for (int u = 0; u < B; u++) sT[tid + jj[u] * NT].y = fmaf(sgn, weight(tq[u], cd.k, cd.kx, cd.ky, cd.lawk), tq[u].y);
+            };
+            while (mf) {                                  // warp-uniform; the candidate's own group is never far (distance 0)
+                const int left = __popc(mf);
+                if (left >= 4) batch_far(std::integral_constant<int, 4>());
+                else if (left == 3) batch_far(std::integral_constant<int, 3>());
+                else if (left == 2) batch_far(std::integral_constant<int, 2>());
+                else batch_far(std::integral_constant<int, 1>());
             }
         } else {
             for (int j = 0; j < ept; j++) {
