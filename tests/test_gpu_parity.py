@@ -293,7 +293,10 @@ def test_fp64_sweeps_follow_the_cpu_twin(geom, detect, sample_ab):
                                                  (O.GEOM_COORDS, 300, 2, 41, None),
                                                  # above 3,000 patches the spatially culled scan (k_sweep_y_cull) and the culled k_conn run
                                                  (O.GEOM_COORDS, 6000, 2, 4, None), (O.GEOM_LINEAR, 5200, 2, 3, None),
-                                                 (O.GEOM_COORDS, 4100, 3, 5, "dieoff")])
+                                                 (O.GEOM_COORDS, 4100, 3, 5, "dieoff"),
+                                                 # beyond one CTA's shared memory in both precisions: FP32 cluster of 8 x 256 threads with 4
+                                                 # candidates per exchange, FP64 scan with its per-task state in global scratch
+                                                 (O.GEOM_COORDS, 40000, 1, 3, None), (O.GEOM_COORDS, 20000, 2, 3, None)])
 def test_fp32_fast_sweep_agrees_with_fp64_path(geom, n, C, T, variant):
     """The FP32 throughput sweep (cluster-split, two-float S, product-of-factors logs) draws from the
     same thresholds as the FP64 path: after one sweep from the same state the latent states agree
@@ -458,6 +461,28 @@ def test_sharded_chain_equals_single_engine(n):
         assert (got[1][0] == want[1][0]).all() and (got[1][1] == want[1][1]).all()
         assert (got[2] == want[2]).all()
         e.close()
+
+
+def test_fp64_sweeps_follow_the_cpu_twin_beyond_shared_memory():
+    """14,500 patches: the FP64 parity scan keeps its per-task state in global scratch (one CTA's shared memory ends at about
+    13,600) and still follows the CPU twin draw by draw."""
+    rng = np.random.default_rng(8)
+    n, T, C = 14500, 3, 1
+    spec, z, _ = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.5, miss=0.05)
+    m = make_model(spec)
+    kw = dict(sample_alpha=1, sample_b=1, alpha_min=1e-4, alpha_max=5e-2, c_max=1.0, n_adapt=2)
+    par0 = pdict(e=0.4, c=0.01, alpha=1 / 400, b=0.5)
+    ch = O.Chains(m, O.sampler_cfg(**kw), C, seed=99, par0=oparams(par0), disperse=False)
+    want = ch.run(2)
+    with make_engine(spec, n_chains=C, seed=99, max_draws=2) as eng:
+        eng.set_params([par0] * C)
+        eng.init_chains(mb.engine.sampler_config(**kw), disperse=False)
+        eng.sweep(2)
+        got = eng.get_draws()
+        zg, yg = eng.get_state()
+    assert (zg == ch.z).all() and (yg == ch.y).all()
+    rel_close(got[:, :, :5], want[:, :, :5], 1e-9)
+    rel_close(got[:, :, 5], want[:, :, 5], 1e-9, floor=1.0)
 
 
 @pytest.mark.parametrize("variant", ["dieoff", "loss"])
