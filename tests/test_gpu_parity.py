@@ -428,6 +428,28 @@ def test_large_landscape_sweep_is_consistent():
     assert np.isfinite(d[:, :, 5]).all() and (yy != y[None]).sum() > 1000
 
 
+def test_cluster_is_widened_until_the_targets_fit_shared_memory():
+    """N = 20,000 with 120 (chain, year) tasks: 1,024 threads per task, and the cost model alone would pick one CTA per task
+    (120 tasks on 148 SMs) whose 20 slots x 1,024 threads x 16 B do not fit an SM -- the launcher must widen the cluster
+    instead of refusing the size.  The sweep runs, S stays consistent with a recomputation, the state stays feasible."""
+    rng = np.random.default_rng(2020)
+    n, T, C = 20000, 16, 8
+    spec, z, y = random_landscape(rng, n, T, O.GEOM_COORDS, occ=0.45, miss=0.02, areas=False)
+    par = pdict(e=0.3, c=0.004, alpha=1 / 400)
+    with make_engine(spec, n_chains=C, precision=mb.FP32, seed=8, max_draws=1) as eng:
+        eng.set_params([par] * C)
+        eng.set_state(np.stack([z] * C), np.stack([y] * C))
+        eng.set_sampler(mb.engine.sampler_config(n_adapt=0))
+        eng.connectivity(fetch=False)
+        eng.sweep(1)
+        geo = eng.scan_geometry()
+        zz, yy = eng.get_state()
+        S_inc = eng.get_connectivity(); S_new = eng.connectivity()
+    assert geo["threads_per_task"] == 1024 and geo["cluster"] >= 2 and geo["culled"], geo
+    rel_close(S_inc, S_new, 1e-6, floor=1e-9)
+    assert ((yy <= zz[:, :-1]) & (yy <= zz[:, 1:])).all() and (yy != np.stack([y] * C)).sum() > 1000
+
+
 @pytest.mark.parametrize("n", [3000, 5200])          # 5200: the culled scan and the culled k_conn run sharded
 def test_sharded_chain_equals_single_engine(n):
     """BASELINE config 5 path: one chain sharded over W ranks (connectivity by target patches, y scan by
