@@ -167,6 +167,46 @@ def test_block_scan_falls_back_to_whole_years_when_the_halo_is_too_small():
     assert (res[0][0] != res[1][0]).sum() <= max(2, 1e-3 * cand), (res[0][0] != res[1][0]).sum()
 
 
+def test_block_scan_with_a_marginal_halo_mixes_block_and_whole_year_scans():
+    """A halo sized for the landscape's typical S but not for its smallest: the years whose smallest S is too small for it are
+    scanned as a whole, the others by blocks, inside the same sweeps -- and the run agrees with the all-whole-year run (halo 0)
+    up to FP32 ties, with S consistent with a recomputation."""
+    rng = np.random.default_rng(23)
+    nside, T, C = 145, 7, 1
+    spec, z, y = wide_landscape(rng, nside, T)
+    par = pdict(e=0.35, c=0.05, alpha=ALPHA, b=0.5)
+    sc = mb.engine.sampler_config(sample_e=0, sample_c=0, update_z=0, n_adapt=0)
+    with make_engine(spec, n_chains=C, precision=mb.FP32, seed=3) as eng:
+        eng.set_params([par] * C)
+        eng.set_state(np.stack([z] * C), np.stack([y] * C))
+        S0 = eng.connectivity()[0]
+    smin = np.sort(S0.min(axis=1))                                      # smallest S of every year
+    apow = float(np.max(spec["area"] ** par["b"]))
+    # the halo that is just enough for the year with the median smallest S
+    halo = (36.0 * np.log(2.0) + np.log(apow / smin[len(smin) // 2])) / ALPHA * 1.0001
+    ext = float(np.ptp(spec["px"]))
+    nx = int(np.floor(2 * ext / (2.0 * halo) * 0.999))                  # k = 3
+    assert nx >= 3, (nx, halo)
+    res = []
+    for h in (halo, 0.0):
+        with make_engine(spec, n_chains=C, precision=mb.FP32, seed=3, max_draws=2) as eng:
+            eng.set_scan_blocks(nx, nx, 3, h)
+            eng.set_params([par] * C)
+            eng.set_state(np.stack([z] * C), np.stack([y] * C))
+            eng.set_sampler(sc)
+            eng.connectivity(fetch=False)
+            eng.work_counters(reset=True)
+            eng.sweep(2)
+            S_inc = eng.get_connectivity()
+            res.append((eng.get_state()[1], S_inc, eng.work_counters()["scan_blocks"], eng.connectivity()))
+    full = 2 * C * (T - 1) * nx * nx
+    assert 0 < res[0][2] < full, (res[0][2], full)                      # some years by blocks, some as a whole
+    assert res[1][2] == 0
+    cand = ((z[:-1] & z[1:]) == 1).sum() * C
+    assert (res[0][0] != res[1][0]).sum() <= max(2, 1e-3 * cand), (res[0][0] != res[1][0]).sum()
+    rel_close(res[0][1], res[0][3], 1e-6, floor=1e-9)
+
+
 def test_sharded_chain_with_blocks_equals_single_engine():
     """One chain over 3 emulated ranks (connectivity by target patches, scan by years) with the block grid on: the
     per-year block decisions depend on the year's own data only, so the sharded run equals the single engine bit for bit."""
