@@ -10,6 +10,21 @@ using namespace mp;
 
 static thread_local std::string g_create_error;
 
+// device copies of the sweep and draw counters (after the host changed them: mp_init_chains, mp_reset_draws)
+static int push_counters(mp_engine *h)
+{
+    CK(cudaSetDevice(h->cfg.device));
+    const uint32_t v[2] = { h->sweep, (uint32_t)h->ndraws };
+    CK(cudaMemcpyAsync(h->d_ctr, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MP_OK;
+}
+// captured sweeps depend on everything a launch takes by value: drop them whenever a setter changes the engine
+static void drop_graphs(mp_engine *h)
+{
+    for (int v = 0; v < 2; v++) { if (h->gexec[v]) { cudaGraphExecDestroy(h->gexec[v]); h->gexec[v] = nullptr; } h->gwarm[v] = false; }
+}
+
 static SamplerDev sampler_dev(const mp_engine *h)
 {
     SamplerDev sd;
@@ -138,7 +153,7 @@ template <typename R, int GEOM> static int launch_sweep_y_g(mp_engine *h)
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nthr = (int)std::min<size_t>(NT, ((nN(h) + 31) / 32) * 32);
     kern<<<ntask, nthr, smem, h->stream>>>(
-        sampler_dev(h), h->sweep, view<R>(h), h->d_par, (const R *)h->d_aw[0], h->have_era ? h->d_era : nullptr, h->d_z,
+        sampler_dev(h), h->d_ctr, view<R>(h), h->d_par, (const R *)h->d_aw[0], h->have_era ? h->d_era : nullptr, h->d_z,
         h->d_y, h->d_S[0], h->cfg.n_years, (const int *)h->d_scan, h->d_work, spill ? h->d_scan_work : nullptr, stride);
     CK(cudaGetLastError());
     return MP_OK;
@@ -167,7 +182,7 @@ static int launch_sweep_y_fast(mp_engine *h)
         Timed tm(h, MP_K_SMALL);
         const int ntask = (C * ntrans - h->task_first + h->task_stride - 1) / h->task_stride;
         if (ntask <= 0) return MP_OK;
-        k_build_candidates<<<ntask, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->sweep, view<float>(h),
+        k_build_candidates<<<ntask, 1024, 0, h->stream>>>(h->cfg.seed, h->cfg.chain_offset, h->d_ctr, view<float>(h),
                                                            (const float *)h->d_aw[0], h->d_z, h->d_y, (CandRec *)h->d_cand,
                                                            h->d_cand_count, h->cfg.n_years, h->geom == MP_GEOM_COORDS,
                                                            h->task_first, h->task_stride, h->d_scan, h->d_minv);
@@ -241,7 +256,7 @@ template <typename R> static int launch_update_z(mp_engine *h)
     Timed tm(h, MP_K_SWEEP_Z);
     const long long cells = (long long)zcells(h);
     dim3 grid((unsigned)std::min<long long>((cells + 255) / 256, 2048), h->cfg.n_chains);
-    k_update_z<R><<<grid, 256, 0, h->stream>>>(sampler_dev(h), h->sweep, view<R>(h), h->d_par, h->d_obs,
+    k_update_z<R><<<grid, 256, 0, h->stream>>>(sampler_dev(h), h->d_ctr, view<R>(h), h->d_par, h->d_obs,
                                                h->have_era ? h->d_era : nullptr, h->d_z, h->d_y, h->d_S[0], h->cfg.n_years);
     CK(cudaGetLastError());
     return MP_OK;
@@ -281,7 +296,7 @@ template <typename R> static int loglik_resident(mp_engine *h, double *d_draw_ro
     if ((rc = launch_col<R>(h, 1, h->d_par, h->d_S[0], h->d_par, h->d_S[0])) != MP_OK) return rc;
     Timed tm(h, MP_K_SMALL);
     k_record<<<h->cfg.n_chains, 32, 0, h->stream>>>(sampler_dev(h), h->d_par, h->d_counts, h->d_partial[0], h->nblk_col,
-                                                    d_draw_row, d_parts);
+                                                    d_draw_row, d_parts, nullptr, 0);
     CK(cudaGetLastError());
     return MP_OK;
 }
@@ -304,7 +319,7 @@ template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
     if (do_ab) {
         { Timed tm(h, MP_K_SMALL);
-          k_propose_ab<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
+          k_propose_ab<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->d_ctr, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
           CK(cudaGetLastError()); }
         if ((rc = launch_area_weights<R>(h, 1)) != MP_OK) return rc;
     }
@@ -339,7 +354,7 @@ template <typename R> static int phase_decide_z(mp_engine *h)
     }
     if ((rc = launch_col<R>(h, do_ab ? 2 : 1, h->d_par, h->d_S[0], h->d_prop, h->d_S[1])) != MP_OK) return rc;
     { Timed tm(h, MP_K_SMALL);
-      k_decide_ab<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
+      k_decide_ab<<<C, 32, 0, h->stream>>>(sd, h->d_ctr, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
                                            h->d_partial[0], h->d_partial[1], h->nblk_col, h->d_llc, do_ab ? 1 : 0, h->d_ljac);
       CK(cudaGetLastError()); }
     if (do_ab) {
@@ -352,12 +367,12 @@ template <typename R> static int phase_decide_z(mp_engine *h)
     if (h->sc.sample_c)
         for (int s = 0; s < h->sc.n_c_steps; s++) {
             { Timed tm(h, MP_K_SMALL);
-              k_propose_c<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, s, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
+              k_propose_c<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->d_ctr, s, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
               CK(cudaGetLastError()); }
             // set 0 := the proposal => partial[0] holds the proposal's sums
             if ((rc = launch_col<R>(h, 1, h->d_prop, h->d_S[0], h->d_prop, h->d_S[0])) != MP_OK) return rc;
             Timed tm(h, MP_K_SMALL);
-            k_decide_c<<<C, 32, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
+            k_decide_c<<<C, 32, 0, h->stream>>>(sd, h->d_ctr, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
                                                 h->d_partial[0], h->nblk_col, h->d_llc);
             CK(cudaGetLastError());
         }
@@ -369,11 +384,11 @@ template <typename R> static int phase_decide_z(mp_engine *h)
             if (!on) continue;
             for (int s = 0; s < h->sc.n_v_steps; s++) {
                 { Timed tm(h, MP_K_SMALL);
-                  k_propose_var<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, which, s, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
+                  k_propose_var<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->d_ctr, which, s, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu, C);
                   CK(cudaGetLastError()); }
                 if ((rc = launch_col<R>(h, 1, h->d_prop, h->d_S[0], h->d_prop, h->d_S[0])) != MP_OK) return rc;
                 Timed tm(h, MP_K_SMALL);
-                k_decide_var<<<C, 32, 0, h->stream>>>(sd, h->sweep, which, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
+                k_decide_var<<<C, 32, 0, h->stream>>>(sd, h->d_ctr, which, h->d_par, h->d_prop, h->d_lsig, h->d_flags, h->d_logu,
                                                       h->d_partial[0], h->nblk_col, h->d_llc, h->d_counts);
                 CK(cudaGetLastError());
             }
@@ -396,16 +411,19 @@ template <typename R> static int phase_finish(mp_engine *h)
     const SamplerDev sd = sampler_dev(h);
     if ((rc = launch_counts(h)) != MP_OK) return rc;
     { Timed tm(h, MP_K_SMALL);
-      k_update_ep<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->sweep, h->d_par, h->d_lsig, h->d_counts, C);
+      k_update_ep<<<(C + 63) / 64, 64, 0, h->stream>>>(sd, h->d_ctr, h->d_par, h->d_lsig, h->d_counts, C);
       CK(cudaGetLastError()); }
     if ((rc = launch_col<R>(h, 1, h->d_par, h->d_S[0], h->d_par, h->d_S[0])) != MP_OK) return rc;
     {
         Timed tm(h, MP_K_SMALL);
-        double *row = h->ndraws < h->cfg.max_draws ? h->d_draws + (size_t)h->ndraws * C * MP_NDRAW : nullptr;
-        k_record<<<C, 32, 0, h->stream>>>(sd, h->d_par, h->d_counts, h->d_partial[0], h->nblk_col, row, nullptr);
+        // the row is chosen on the device from the draw counter, and the counters advance there too: the launches of a sweep carry
+        // no per-sweep host value, so a captured sweep can be replayed (mp_sweep)
+        k_record<<<C, 32, 0, h->stream>>>(sd, h->d_par, h->d_counts, h->d_partial[0], h->nblk_col, h->d_draws, nullptr, h->d_ctr, h->cfg.max_draws);
         CK(cudaGetLastError());
-        if (row) h->ndraws++;
+        k_advance<<<1, 1, 0, h->stream>>>(h->d_ctr, h->cfg.max_draws);
+        CK(cudaGetLastError());
     }
+    if (h->ndraws < h->cfg.max_draws) h->ndraws++;          // host mirrors of the device counters
     h->sweep++;
     return MP_OK;
 }
@@ -438,11 +456,12 @@ int mp_destroy(mp_engine *h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm) mp_comm_destroy(h);
+    drop_graphs(h);
     drain_spans(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     void *ptrs[] = { h->d_area, h->d_src_unit, h->d_px, h->d_py, h->d_dist, h->d_obs, h->d_era, h->d_par, h->d_prop,
                      h->d_lsig, h->d_z, h->d_y, h->d_srec, h->d_S[0], h->d_S[1], h->d_aw[0], h->d_aw[1], h->d_partial[0],
-                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_scan, h->d_minv, h->d_tile_box, h->d_mlow, h->d_work, h->d_gemm, h->d_tlist, h->d_btasks, h->d_blockmode, h->d_scan_work, h->d_comm_send, h->d_comm_recv };
+                     h->d_partial[1], h->d_llc, h->d_logu, h->d_parts, h->d_scalar, h->d_flags, h->d_counts, h->d_draws, h->d_cand, h->d_cand_count, h->d_task_order, h->d_ljac, h->d_perm, h->d_scan, h->d_minv, h->d_tile_box, h->d_mlow, h->d_work, h->d_gemm, h->d_tlist, h->d_btasks, h->d_blockmode, h->d_scan_work, h->d_comm_send, h->d_comm_recv, h->d_ctr };
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -481,6 +500,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
+    if (const char *env = getenv("MP_GRAPH")) h->use_graph = atoi(env) != 0;
     if (const char *env = getenv("MP_BLK_TPT")) { const int v = atoi(env); if (v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->blk_tpt = v; }
     if (const char *env = getenv("MP_BLK_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) h->blk_cs = v; }
     h->sm_count = prop.multiProcessorCount;
@@ -510,7 +530,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
         { (void **)&h->d_draws, std::max<size_t>(1, (size_t)cfg->max_draws) * C * MP_NDRAW * 8 },
         { &h->d_cand, cfg->precision == MP_FP32 ? C * (T - 1) * N * sizeof(CandRec) : 32 },
         { (void **)&h->d_cand_count, C * (T - 1) * 2 * sizeof(int) }, { (void **)&h->d_task_order, C * (T - 1) * sizeof(int) },
-        { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_scan, N * sizeof(int) }, { (void **)&h->d_minv, N * sizeof(int) }, { (void **)&h->d_work, MP_CNT_N * sizeof(unsigned long long) },
+        { (void **)&h->d_ctr, 2 * sizeof(uint32_t) }, { (void **)&h->d_perm, N * sizeof(int) }, { (void **)&h->d_scan, N * sizeof(int) }, { (void **)&h->d_minv, N * sizeof(int) }, { (void **)&h->d_work, MP_CNT_N * sizeof(unsigned long long) },
         { (void **)&h->d_tile_box, ((N + 31) / 32) * sizeof(float4) }, { (void **)&h->d_mlow, C * ((N + 31) / 32) * sizeof(float) },
     };
     for (auto &r : reqs) {
@@ -533,7 +553,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
 // ---- landscape
 // Uploads below use the blocking default stream; the engine stream is non-blocking, so wait for its
 // pending work first (a setter called after an asynchronous mp_sweep must not race with it).
-static int quiesce(mp_engine *h) { CK(cudaStreamSynchronize(h->stream)); return MP_OK; }
+static int quiesce(mp_engine *h) { CK(cudaStreamSynchronize(h->stream)); drop_graphs(h); return MP_OK; }
 static int upload_real(mp_engine *h, void *dst, const double *src, size_t n)
 {
     if (is64(h)) { CK(cudaMemcpy(dst, src, n * 8, cudaMemcpyHostToDevice)); return MP_OK; }
@@ -951,6 +971,7 @@ int mp_set_sampler(mp_engine *h, const mp_sampler_config *sc)
     REQUIRE(!sc->sample_K || (sc->K_min > 0 && sc->K_max >= sc->K_min), MP_ERR_ARG, "sample_K needs 0 < K_min <= K_max");
     REQUIRE(!sc->sample_Ksrc || (sc->Ksrc_min > 0 && sc->Ksrc_max >= sc->Ksrc_min), MP_ERR_ARG, "sample_Ksrc needs 0 < Ksrc_min <= Ksrc_max");
     h->sc = *sc; h->have_sc = true;
+    drop_graphs(h);
     return MP_OK;
 }
 int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
@@ -1002,6 +1023,7 @@ int mp_init_chains(mp_engine *h, const mp_sampler_config *sc, int disperse)
     if ((rc = mp_set_params(h, par.data())) != MP_OK) return rc;
     if ((rc = mp_set_state(h, z.data(), y.data())) != MP_OK) return rc;
     h->sweep = 0; h->ndraws = 0;
+    if ((rc = push_counters(h)) != MP_OK) return rc;
     // the sampler's resident S always comes from k_conn: its FP64 accumulation is what lets rank-1 removals cancel exactly
     if ((rc = check_ready(h)) != MP_OK) return rc;
     if ((rc = is64(h) ? refresh_S<double>(h, false) : refresh_S<float>(h, false)) != MP_OK) return rc;
@@ -1045,6 +1067,37 @@ int mp_sweep(mp_engine *h, int nsweeps)
     REQUIRE(h->have_sc && h->have_obs, MP_ERR_STATE, "sampler not configured (mp_init_chains / mp_set_sampler)");
     h->par_host_valid = false;                           // the sampler moves the parameters on the device
     for (int s = 0; s < nsweeps; s++) {
+        // A sweep is ~20 launches that carry no per-sweep host value (the kernels read the sweep and draw counters from device
+        // memory), so it is captured once per kind -- without / with the refresh of the resident S -- and replayed as a CUDA
+        // graph: on small landscapes the sweep is launch-bound.  The first sweep of a kind runs eagerly (lazy allocations).
+        const bool whole = h->conn_hi < 0 && h->task_first == 0 && h->task_stride == 1;
+        if (h->use_graph && !h->timing && h->S_valid && whole) {
+            const int v = (is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0) ? 1 : 0;
+            if (!h->gexec[v] && h->gwarm[v]) {
+                const uint32_t sweep0 = h->sweep; const int ndraws0 = h->ndraws;
+                long long before[MP_K_NCAT];
+                for (int i = 0; i < MP_K_NCAT; i++) before[i] = h->t_launch[i];
+                cudaGraph_t g = nullptr;
+                bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    rc = is64(h) ? sweep_once<double>(h) : sweep_once<float>(h);
+                    ok = cudaStreamEndCapture(h->stream, &g) == cudaSuccess && rc == MP_OK && g != nullptr;
+                    if (ok) ok = cudaGraphInstantiate(&h->gexec[v], g, 0) == cudaSuccess;
+                    if (g) cudaGraphDestroy(g);
+                }
+                h->sweep = sweep0; h->ndraws = ndraws0;       // nothing ran yet: the capture only advanced the host mirrors ...
+                for (int i = 0; i < MP_K_NCAT; i++) { h->glaunch[v][i] = h->t_launch[i] - before[i]; h->t_launch[i] = before[i]; }   // ... and the launch counts, which every replay adds
+                if (!ok) { cudaGetLastError(); h->gexec[v] = nullptr; h->use_graph = 0; }
+            }
+            if (h->gexec[v]) {
+                CK(cudaGraphLaunch(h->gexec[v], h->stream));
+                for (int i = 0; i < MP_K_NCAT; i++) h->t_launch[i] += h->glaunch[v][i];
+                if (h->ndraws < h->cfg.max_draws) h->ndraws++;
+                h->sweep++;
+                continue;
+            }
+            h->gwarm[v] = true;
+        }
         rc = is64(h) ? sweep_once<double>(h) : sweep_once<float>(h);
         if (rc != MP_OK) return rc;
         if (h->timing && h->spans.size() > 16384) { CK(cudaStreamSynchronize(h->stream)); drain_spans(h); }
@@ -1062,6 +1115,7 @@ int mp_set_shard(mp_engine *h, int conn_lo, int conn_hi, int task_first, int tas
             "mp_set_shard: conn_lo and conn_hi must be multiples of 256 (conn_hi may also be n_patches)");
     h->conn_lo = conn_hi < 0 ? 0 : conn_lo; h->conn_hi = conn_hi; h->task_first = task_first; h->task_stride = task_stride;
     h->blk_tasks_dirty = true;
+    drop_graphs(h);
     return MP_OK;
 }
 int mp_sweep_phase(mp_engine *h, int phase, int *flags_out)
@@ -1175,7 +1229,7 @@ int mp_synchronize(mp_engine *h)
 }
 int mp_num_draws(mp_engine *h) { return h ? h->ndraws : MP_ERR_ARG; }
 int mp_sweep_index(mp_engine *h) { return h ? (int)h->sweep : MP_ERR_ARG; }
-int mp_reset_draws(mp_engine *h) { if (!h) return MP_ERR_ARG; h->ndraws = 0; return MP_OK; }
+int mp_reset_draws(mp_engine *h) { if (!h) return MP_ERR_ARG; h->ndraws = 0; return push_counters(h); }
 int mp_get_draws(mp_engine *h, int first, int count, double *out)
 {
     if (!h || !out) return MP_ERR_ARG;
@@ -1295,6 +1349,7 @@ int mp_set_timing(mp_engine *h, int enabled)
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
     drain_spans(h);
+    drop_graphs(h);
     h->timing = enabled != 0;
     return MP_OK;
 }

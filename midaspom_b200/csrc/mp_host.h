@@ -44,7 +44,12 @@ struct mp_engine {
     unsigned long long *d_counts = nullptr;
     double *d_draws = nullptr;
     int ndraws = 0;
-    uint32_t sweep = 0;
+    uint32_t sweep = 0;              // host mirrors of d_ctr = {sweep, recorded draws}, the counters the kernels read
+    uint32_t *d_ctr = nullptr;
+    cudaGraphExec_t gexec[2] = { nullptr, nullptr };   // a captured sweep without / with the refresh of the resident S (mp_sweep)
+    bool gwarm[2] = { false, false };                  // that kind of sweep has run once eagerly (lazy allocations done)
+    long long glaunch[2][6] = { { 0 } };               // kernel launches per category inside each captured sweep (mp_get_timing counts them per replay)
+    int use_graph = 1;               // replay captured sweeps (MP_GRAPH=0 disables)
     int nblk_col = 1;
     void *d_cand = nullptr;          // candidate records of the FP32 fast sweep (mp::CandRec, 32 B each)
     int *d_cand_count = nullptr;     // [task][2]: candidates, occupied

@@ -137,9 +137,10 @@ struct SamplerDev {
 __device__ __forceinline__ double adapt_gain(uint32_t sweep) { return 1.0 / pow((double)sweep + 1.0, 0.6); }
 
 // flags[c*4+0] = proposal in bounds, +1 = accepted, +2/+3 spare ; logu[c] = log of the MH uniform
-__global__ void k_propose_ab(SamplerDev sd, uint32_t sweep, const mp_params *__restrict__ par, mp_params *__restrict__ prop,
+__global__ void k_propose_ab(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, const mp_params *__restrict__ par, mp_params *__restrict__ prop,
                              const double *__restrict__ lsig, int *__restrict__ flags, double *__restrict__ logu, int nchains)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchains) return;
     const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_AB, 0, 0);
@@ -186,11 +187,12 @@ __global__ void k_ridge_c(SamplerDev sd, const mp_params *__restrict__ par, mp_p
     ljac[c] = lj;
 }
 // llc[c] receives the colonisation log-likelihood of the state kept
-__global__ void k_decide_ab(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
+__global__ void k_decide_ab(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
                             double *__restrict__ lsig, int *__restrict__ flags, const double *__restrict__ logu,
                             const double *__restrict__ part_cur, const double *__restrict__ part_prop, int nblk,
                             double *__restrict__ llc, int do_mh, const double *__restrict__ ljac)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x;
     const double cur = reduce_partials(part_cur + (size_t)c * nblk, nblk);
     double pr = 0.0;
@@ -222,10 +224,11 @@ __global__ void k_commit_ab(const int *__restrict__ flags, double *__restrict__ 
         if (i < n) aw_cur[(size_t)c * n + i] = aw_prop[(size_t)c * n + i];
     }
 }
-__global__ void k_propose_c(SamplerDev sd, uint32_t sweep, int step, const mp_params *__restrict__ par,
+__global__ void k_propose_c(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, int step, const mp_params *__restrict__ par,
                             mp_params *__restrict__ prop, const double *__restrict__ lsig, int *__restrict__ flags,
                             double *__restrict__ logu, int nchains)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchains) return;
     const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_C, (uint32_t)step, 0);
@@ -237,10 +240,11 @@ __global__ void k_propose_c(SamplerDev sd, uint32_t sweep, int step, const mp_pa
     flags[c * 4 + 0] = q.c >= sd.sc.c_min && q.c <= sd.sc.c_max;
     logu[c] = log(u01(r.z));
 }
-__global__ void k_decide_c(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
+__global__ void k_decide_c(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
                            double *__restrict__ lsig, const int *__restrict__ flags, const double *__restrict__ logu,
                            const double *__restrict__ part_prop, int nblk, double *__restrict__ llc)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x;
     const double pr = reduce_partials(part_prop + (size_t)c * nblk, nblk);
     if (threadIdx.x != 0) return;
@@ -250,10 +254,11 @@ __global__ void k_decide_c(SamplerDev sd, uint32_t sweep, mp_params *__restrict_
     if (sweep < (uint32_t)sd.sc.n_adapt) lsig[c * MP_NLSIG + 1] += adapt_gain(sweep) * (acc - 0.44);
 }
 // variant parameters: which = 0 K (log random walk), 1 Ksrc (log random walk), 2 dsrc (additive)
-__global__ void k_propose_var(SamplerDev sd, uint32_t sweep, int which, int step, const mp_params *__restrict__ par,
+__global__ void k_propose_var(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, int which, int step, const mp_params *__restrict__ par,
                               mp_params *__restrict__ prop, const double *__restrict__ lsig, int *__restrict__ flags,
                               double *__restrict__ logu, int nchains)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchains) return;
     const uint4 r = rng(sd.seed, (uint32_t)(sd.chain_offset + c), sweep, RK_K + (uint32_t)which, (uint32_t)step, 0);
@@ -268,11 +273,12 @@ __global__ void k_propose_var(SamplerDev sd, uint32_t sweep, int which, int step
     flags[c * 4 + 0] = inb;
     logu[c] = log(u01(r.z));
 }
-__global__ void k_decide_var(SamplerDev sd, uint32_t sweep, int which, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
+__global__ void k_decide_var(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, int which, mp_params *__restrict__ par, const mp_params *__restrict__ prop,
                              double *__restrict__ lsig, const int *__restrict__ flags, const double *__restrict__ logu,
                              const double *__restrict__ part_prop, int nblk, double *__restrict__ llc,
                              const unsigned long long *__restrict__ counts)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x;
     const double pr = reduce_partials(part_prop + (size_t)c * nblk, nblk);
     if (threadIdx.x != 0) return;
@@ -283,9 +289,10 @@ __global__ void k_decide_var(SamplerDev sd, uint32_t sweep, int which, mp_params
     if (sweep < (uint32_t)sd.sc.n_adapt) lsig[c * MP_NLSIG + 5 + which] += adapt_gain(sweep) * (acc - 0.44);
 }
 // e and p from the sufficient counts: random-walk MH sub-steps, one thread per chain
-__global__ void k_update_ep(SamplerDev sd, uint32_t sweep, mp_params *__restrict__ par, double *__restrict__ lsig,
+__global__ void k_update_ep(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, mp_params *__restrict__ par, double *__restrict__ lsig,
                             const unsigned long long *__restrict__ counts, int nchains)
 {
+    const uint32_t sweep = *sweep_p;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchains) return;
     const unsigned long long *cn = counts + (size_t)c * NCOUNT;
@@ -329,10 +336,13 @@ __global__ void k_update_ep(SamplerDev sd, uint32_t sweep, mp_params *__restrict
     par[c] = p;
 }
 // draws[c] = (e, c, alpha, b, p, loglik, #y=1, #z=1); parts (nullable) = ext, col, prior, det
+// ctr (nullable): {sweep, recorded draws}; with it the row is draws + ctr[1] * chains * MP_NDRAW while ctr[1] < max_draws
 __global__ void k_record(SamplerDev sd, const mp_params *__restrict__ par, const unsigned long long *__restrict__ counts,
-                         const double *__restrict__ part_cur, int nblk, double *__restrict__ draw, double *__restrict__ parts)
+                         const double *__restrict__ part_cur, int nblk, double *__restrict__ draw, double *__restrict__ parts,
+                         const uint32_t *__restrict__ ctr, int max_draws)
 {
     const int c = blockIdx.x;
+    if (ctr) draw = (int)ctr[1] < max_draws ? draw + (size_t)ctr[1] * gridDim.x * MP_NDRAW : nullptr;
     const double lc = reduce_partials(part_cur + (size_t)c * nblk, nblk);
     if (threadIdx.x != 0) return;
     const unsigned long long *cn = counts + (size_t)c * NCOUNT;
@@ -346,14 +356,22 @@ __global__ void k_record(SamplerDev sd, const mp_params *__restrict__ par, const
     if (parts) { double *q = parts + (size_t)c * MP_NPART; q[0] = le; q[1] = lc; q[2] = lp; q[3] = ld; }
 }
 
+// end of a sweep: the device-resident counters every kernel of the next sweep reads (so that a captured sweep can be replayed)
+static __global__ void k_advance(uint32_t *__restrict__ ctr, int max_draws)
+{
+    if ((int)ctr[1] < max_draws) ctr[1]++;
+    ctr[0]++;
+}
+
 // ------------------------------------------------------------------ latent occupancy cells
 // z_tk | y, theta for every latent cell at once: S depends on y only, so the cells are
 // conditionally independent.  Forced to 1 when an adjacent intermediate state is 1.
 template <typename R>
-__global__ void k_update_z(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par,
+__global__ void k_update_z(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, Landscape<R> ls, const mp_params *__restrict__ par,
                            const int8_t *__restrict__ obs, const uint8_t *__restrict__ era, uint8_t *__restrict__ z,
                            const uint8_t *__restrict__ y, const double *__restrict__ S, int T)
 {
+    const uint32_t sweep = *sweep_p;
     const int n = ls.n, c = blockIdx.y, ntrans = T - 1;
     const long long cells = (long long)T * n;
     const mp_params p = par[c];
@@ -447,13 +465,14 @@ __global__ void k_flip_delta(Landscape<R> ls, const mp_params *__restrict__ par,
 // takes the same decision from logit(u) < delta with u = Philox(seed, chain, sweep, RK_Y, k, t).
 template <typename R, int GEOM, int NT>
 __global__ void __launch_bounds__(NT, 1)
-k_sweep_y(SamplerDev sd, uint32_t sweep, Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
+k_sweep_y(SamplerDev sd, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter (k_advance) */, Landscape<R> ls, const mp_params *__restrict__ par, const R *__restrict__ aw,
           const uint8_t *__restrict__ era, const uint8_t *__restrict__ z, uint8_t *__restrict__ y, double *__restrict__ S, int T,
           const int *__restrict__ order /* visiting order of the scan: slot -> patch (oracle: spom_scan_order) */,
           unsigned long long *__restrict__ stats,
           unsigned char *__restrict__ work /* landscapes beyond one CTA's shared memory: per-task scratch in global memory (L2 resident), else nullptr */,
           size_t work_stride)
 {
+    const uint32_t sweep = *sweep_p;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x, nthr = blockDim.x;
     const int c = blockIdx.x / ntrans, t = blockIdx.x - c * ntrans;

@@ -91,12 +91,13 @@ __device__ __forceinline__ float warp_sum_f(float v)
 // ------------------------------------------------------------------ candidate records
 // One CTA per (chain, transition): candidates in patch order, compacted by a block scan.
 static __global__ void __launch_bounds__(1024)
-k_build_candidates(uint64_t seed, int chain_offset, uint32_t sweep, Landscape<float> ls, const float *__restrict__ aw,
+k_build_candidates(uint64_t seed, int chain_offset, const uint32_t *__restrict__ sweep_p /* device-resident sweep counter */, Landscape<float> ls, const float *__restrict__ aw,
                    const uint8_t *__restrict__ z, const uint8_t *__restrict__ y, CandRec *__restrict__ rec,
                    int *__restrict__ count /* [task][2]: candidates, occupied */, int T, int coords, int task_first, int task_stride,
                    const int *__restrict__ scan /* visiting order: position -> patch */, const int *__restrict__ minv /* patch -> layout (Morton) slot */)
 {
     __shared__ int s_cnt[1024], s_occ[32];
+    const uint32_t sweep = *sweep_p;
     const int n = ls.n, ntrans = T - 1, tid = threadIdx.x;
     const int task = task_first + blockIdx.x * task_stride, c = task / ntrans, t = task - c * ntrans;
     const uint8_t *zt = z + ((size_t)c * T + t) * n, *zn = zt + n, *yt = y + ((size_t)c * ntrans + t) * n;
