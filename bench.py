@@ -377,16 +377,29 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         ess_run = time.perf_counter() - t0
     # ---- likelihood evaluations/s (second part of BASELINE's metric): 1 evaluation = full connectivity S of the resident
-    # state + the summed log-terms of one chain, through the public calls mp_connectivity + mp_loglik
+    # state + the summed log-terms of one chain = one chain's share of one mp_loglik call (the call recomputes S
+    # from scratch every time; it is not preceded by mp_connectivity, which would compute the same S a second time)
     barrier()
     n_ll = 10
+    eng.loglik()
     t0 = time.perf_counter()
     for _ in range(n_ll):
-        eng.connectivity(fetch=False)
         eng.loglik()
     barrier()
     (t_ll,) = max_over_ranks([time.perf_counter() - t0])
     lik_evals = chains_total * n_ll / t_ll
+    # the same through host buffers: parameters, z and y of every chain go in with the call (mp_loglik_host), per-chain sums come back
+    par_h = eng.get_params()
+    z_h, y_h = eng.get_state()
+    eng.loglik_host(par_h, z_h, y_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_ll):
+        eng.loglik_host(par_h, z_h, y_h)
+    barrier()
+    (t_ll_h,) = max_over_ranks([time.perf_counter() - t0])
+    lik_evals_host = dict(value=chains_total * n_ll / t_ll_h, h2d_bytes_per_call=int(z_h.nbytes + y_h.nbytes),
+                          note="mp_loglik_host: z and y of every chain copied from (pageable) host arrays inside the timed call")
     # posterior diagnostics on everything recorded so far (gathered over ranks with NCCL)
     nd = eng.num_draws()
     d_local = torch.from_numpy(eng.get_draws(0, nd)).to(dev)
@@ -405,11 +418,10 @@ def run_ours(args, rank, local_rank, world):
     # tensor cores (k_conn_gemm: tcgen05.mma + TMEM + TMA); every chain gets chain 0's current parameters
     p0 = eng.get_params()[0]
     eng.set_params([p0] * cpg)
-    eng.connectivity(fetch=False); eng.loglik()
+    eng.loglik()
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_ll):
-        eng.connectivity(fetch=False)
         eng.loglik()
     barrier()
     (t_ll_g,) = max_over_ranks([time.perf_counter() - t0])
@@ -463,7 +475,8 @@ def run_ours(args, rank, local_rank, world):
                     kernel_ms={k: round(v, 4) for k, v in kms.items()}, kernel_launches=klaunch,
                     kernel_split_note=f"separate pass of {K} steps with per-kernel CUDA events on ({split_total / K:.3f} ms per step); `value` is timed with them off",
                     wall_s_timed_region=t_wall,
-                    likelihood_evals_per_sec=lik_evals, likelihood_evals_per_sec_shared_params=lik_evals_shared,
+                    likelihood_evals_per_sec=lik_evals, likelihood_evals_per_sec_host_buffers=lik_evals_host,
+                    likelihood_evals_per_sec_shared_params=lik_evals_shared,
                     ess_per_sec=ess_min / run_s if run_s > 0 else None,
                     ess=dict(min_ess=ess_min, seconds=run_s, sweeps=(n_ess // 2 if ess_run is not None else nd - W),
                              note="min over sampled parameters of the summed per-chain ESS (Geyer), second half of a separate "

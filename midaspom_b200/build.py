@@ -13,7 +13,7 @@ LIB_DIR = PKG / "lib"
 OBJ_DIR = LIB_DIR / "obj"
 LIB = LIB_DIR / "libmidaspom_cuda.so"
 SOURCES = [CSRC / "mp_engine.cu", CSRC / "mp_sweep_fast_linear.cu", CSRC / "mp_sweep_fast_coords.cu",
-           CSRC / "mp_sweep_fast_dense.cu", CSRC / "mp_exact.cu", CSRC / "mp_conn_gemm.cu", CSRC / "mp_comm.cu"]
+           CSRC / "mp_sweep_fast_dense.cu", CSRC / "mp_exact.cu", CSRC / "mp_conn_gemm.cu", CSRC / "mp_comm.cu", CSRC / "mp_conn32.cu"]
 HEADERS = [CSRC / "mp_device.cuh", CSRC / "mp_kernels.cuh", CSRC / "mp_conn.cuh", CSRC / "mp_sweep_fast.cuh", CSRC / "mp_sweep_cull.cuh", CSRC / "mp_host.h", CSRC / "mp_comm.h",
            PKG.parent / "include" / "libmidaspom_cuda.h"]
 

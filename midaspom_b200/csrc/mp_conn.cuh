@@ -10,13 +10,26 @@
 //                  dispersal weight is evaluated once per (target, source) pair and contracted over the years with
 //                  acc[t] = fma(w, y01[t], acc[t]) (exactly acc[t] + w or acc[t]).  FP64 accumulation in both precisions so
 //                  that later rank-1 removals of the same FP32 weight by the y scan cancel exactly.
+//                  A32 variant (FP32 engines, mp_conn32.cu): the year contraction of each group of 32 sources runs on the
+//                  FP32 pipe as packed FFMA2 (fma.rn.f32x2: two years per instruction) into FP32 partial sums, which join
+//                  the FP64 accumulators (in shared memory, one column per thread) after every group of 32 sources -- half
+//                  the pipe time of the DFMA form and a third of its issue slots.  A partial sum rounds at 2^-24 over at most
+//                  32 terms (bound 2e-6 relative; measured on the cfg3 landscape rms 3.5e-8, max 1.1e-7: far inside the FP32
+//                  path's 1e-5 and below the 2^-30 culling of the same kernel); it is taken per (target, aligned group of 32
+//                  sources), so the result does not depend on the launch shape or on how the targets are sharded.
 #pragma once
+#include <type_traits>
 #include "mp_device.cuh"
 
 namespace mp {
 
 constexpr int CONN_BATCH = 4;      // sources whose weights are evaluated together before their year contractions
 constexpr int CONN_PAD = 128;       // the record stream of a (set, chain, word) is padded to whole tiles (zero records)
+constexpr int CONN_A32_GROUPS = 1;  // A32: groups of 32 sources whose FP32 partial sums are added up before they join the FP64 accumulators
+                                    // (measured on the cfg3 landscape, error of S against the FP64 sum of the same weights: 1 group rms 3.5e-8 /
+                                    // max 1.1e-7, 2 groups 5.6e-8 / 1.8e-7, 4 groups 8.6e-8 / 3.4e-7)
+// dynamic shared memory of the A32 variant: FP64 accumulators [2 targets x NYB years][NTHR threads]
+inline __host__ __device__ size_t conn_a32_smem(int nyb, int nthr) { return (size_t)2 * nyb * nthr * sizeof(double); }
 
 template <typename R> struct SrcRec;
 template <> struct __align__(16) SrcRec<float> { float x, y, aw; uint32_t bits; };
@@ -118,13 +131,33 @@ __device__ __forceinline__ void conn_bulk_load(uint32_t dst_smem, const void *sr
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <typename R, int GEOM, int NYB, bool CULL, int TGT, int NTHR>
+// packed FP32 pairs (sm_100a FFMA2)
+__device__ __forceinline__ unsigned long long conn_pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void conn_unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void conn_ffma2(unsigned long long &acc, unsigned long long a, unsigned long long b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+template <typename R, int GEOM, int NYB, bool CULL, int TGT, int NTHR, bool A32 = false>
 __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
 {
+    static_assert(!A32 || (sizeof(R) == 4 && NYB % 4 == 0), "the FP32 contraction is for FP32 engines, four years per shared-memory load");
+    using YT = typename std::conditional<A32, float, double>::type;
     static_assert(CONN_PAD % NTHR == 0 && NTHR % 32 == 0, "tiles must divide the padding of the record stream");
     __shared__ __align__(128) SrcRec<R> srec[2][NTHR];                // two-stage ring of source tiles (TMA destination)
-    __shared__ __align__(16) double sy01[NTHR][NYB];                  // year bits of the current tile as 0.0 / 1.0
+    __shared__ __align__(16) YT sy01[NTHR][NYB];                      // year bits of the current tile as 0.0 / 1.0
     __shared__ __align__(8) unsigned long long full[2];
+    extern __shared__ __align__(16) unsigned char conn_dyn[];        // A32: the thread's FP64 accumulators, sacc[(g * NYB + t) * NTHR + tid]
+    double *sacc = reinterpret_cast<double *>(conn_dyn) + threadIdx.x;
     const int n = a.ls.n, npad = conn_npad(n), c = blockIdx.y, set = blockIdx.z + a.set_base, tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
     const int slot0 = a.k_lo + blockIdx.x * NTHR * TGT;              // first target slot of the CTA
@@ -196,11 +229,35 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
             conn_mbar_expect_tx(bar, (uint32_t)(NTHR * sizeof(SrcRec<R>)));
             conn_bulk_load(conn_smem_u32(&srec[st][0]), rw + (size_t)tile * NTHR, (uint32_t)(NTHR * sizeof(SrcRec<R>)), bar);
         };
-        double acc[TGT][NYB];
+        double acc[A32 ? 1 : TGT][A32 ? 1 : NYB];
 #pragma unroll
-        for (int g = 0; g < TGT; g++)
+        for (int g = 0; g < (A32 ? 1 : TGT); g++)
 #pragma unroll
-            for (int t = 0; t < NYB; t++) acc[g][t] = 0.0;
+            for (int t = 0; t < (A32 ? 1 : NYB); t++) acc[g][t] = 0.0;
+        // A32: FP32 partial sums of the sources at hand, two years per register pair; the FP64 accumulators live in shared memory
+        unsigned long long part[A32 ? TGT : 1][A32 ? NYB / 2 : 1];
+#pragma unroll
+        for (int g = 0; g < (A32 ? TGT : 1); g++)
+#pragma unroll
+            for (int t = 0; t < (A32 ? NYB / 2 : 1); t++) part[g][t] = 0ull;
+        if constexpr (A32) {
+#pragma unroll
+            for (int i = 0; i < TGT * NYB; i++) sacc[i * NTHR] = 0.0;
+        }
+        int pend = -1;                                               // A32: aligned source group the partial sums belong to (-1: none pending)
+        auto flush = [&]() {
+            if constexpr (A32) {
+#pragma unroll
+                for (int g = 0; g < TGT; g++)
+#pragma unroll
+                    for (int t2 = 0; t2 < NYB / 2; t2++) {
+                        float lo, hi;
+                        conn_unpack2(part[g][t2], lo, hi);
+                        sacc[(g * NYB + 2 * t2) * NTHR] += (double)lo; sacc[(g * NYB + 2 * t2 + 1) * NTHR] += (double)hi;
+                        part[g][t2] = 0ull;
+                    }
+            }
+        };
         bool far[TGT];                                               // culled variant: group g is out of reach of the 32 sources at hand
 #pragma unroll
         for (int g = 0; g < TGT; g++) far[g] = false;
@@ -215,35 +272,69 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
             {
                 const uint32_t bits = sr[tid].bits;
 #pragma unroll
-                for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? 1.0 : 0.0;
+                for (int t = 0; t < NYB; t++) sy01[tid][t] = (bits >> t) & 1u ? YT(1) : YT(0);
             }
             __syncthreads();
             const int l0 = cur * NTHR;
             // CONN_BATCH sources at a time: first all their weights (independent SQRT / EX2 chains that overlap), then the
             // year contraction of each -- the weight latency is paid once per batch, not once per source
-            auto batch = [&](int j0) {
-                double wd[CONN_BATCH][TGT];
+            auto batch = [&](int j0, auto SPECIAL) {
+                // SPECIAL: some weight of this group of 32 sources is forced to zero (the target itself, a target group out
+                // of reach); otherwise the test is not even evaluated (A32; the FP64 form always evaluates it)
+                constexpr bool special = decltype(SPECIAL)::value;
+                if constexpr (A32) {
+                    float wf[CONN_BATCH][TGT];
 #pragma unroll
-                for (int u = 0; u < CONN_BATCH; u++) {
-                    const SrcRec<R> s = sr[j0 + u];                  // broadcast LDS.128
-                    const int lj = l0 + j0 + u;                      // slot of the source (== patch number without coordinates)
-#pragma unroll
-                    for (int g = 0; g < TGT; g++) {
-                        R wgt = pair_weight<R, GEOM>(a.ls, apre, s.aw, kq[g], lj, tx[g], ty[g], s.x, s.y);
-                        if (lj == ks[g] || (CULL && far[g])) wgt = 0;    // l != k  (main_MIDASPOM.c:354)
-                        wd[u][g] = (double)wgt;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < CONN_BATCH; u++) {
-                    const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j0 + u][0]);
-#pragma unroll
-                    for (int t2 = 0; t2 < NYB / 2; t2++) {
-                        const double2 m = yb[t2];
+                    for (int u = 0; u < CONN_BATCH; u++) {
+                        const SrcRec<R> s = sr[j0 + u];              // broadcast LDS.128
+                        const int lj = l0 + j0 + u;
 #pragma unroll
                         for (int g = 0; g < TGT; g++) {
-                            acc[g][2 * t2] = fma(wd[u][g], m.x, acc[g][2 * t2]);
-                            acc[g][2 * t2 + 1] = fma(wd[u][g], m.y, acc[g][2 * t2 + 1]);
+                            float wgt = pair_weight<R, GEOM>(a.ls, apre, s.aw, kq[g], lj, tx[g], ty[g], s.x, s.y);
+                            if (special && (lj == ks[g] || (CULL && far[g]))) wgt = 0.f;
+                            wf[u][g] = wgt;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < CONN_BATCH; u++) {
+                        const ulonglong2 *yb = reinterpret_cast<const ulonglong2 *>(&sy01[j0 + u][0]);
+                        unsigned long long ww[TGT];
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) ww[g] = conn_pack2(wf[u][g], wf[u][g]);
+#pragma unroll
+                        for (int t4 = 0; t4 < NYB / 4; t4++) {
+                            const ulonglong2 m = yb[t4];             // four years of this source
+#pragma unroll
+                            for (int g = 0; g < TGT; g++) {
+                                conn_ffma2(part[g][2 * t4], ww[g], m.x);
+                                conn_ffma2(part[g][2 * t4 + 1], ww[g], m.y);
+                            }
+                        }
+                    }
+                } else {
+                    double wd[CONN_BATCH][TGT];
+#pragma unroll
+                    for (int u = 0; u < CONN_BATCH; u++) {
+                        const SrcRec<R> s = sr[j0 + u];              // broadcast LDS.128
+                        const int lj = l0 + j0 + u;                  // slot of the source (== patch number without coordinates)
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) {
+                            R wgt = pair_weight<R, GEOM>(a.ls, apre, s.aw, kq[g], lj, tx[g], ty[g], s.x, s.y);
+                            if (lj == ks[g] || (CULL && far[g])) wgt = 0;    // l != k  (main_MIDASPOM.c:354)
+                            wd[u][g] = (double)wgt;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < CONN_BATCH; u++) {
+                        const double2 *yb = reinterpret_cast<const double2 *>(&sy01[j0 + u][0]);
+#pragma unroll
+                        for (int t2 = 0; t2 < NYB / 2; t2++) {
+                            const double2 m = yb[t2];
+#pragma unroll
+                            for (int g = 0; g < TGT; g++) {
+                                acc[g][2 * t2] = fma(wd[u][g], m.x, acc[g][2 * t2]);
+                                acc[g][2 * t2 + 1] = fma(wd[u][g], m.y, acc[g][2 * t2 + 1]);
+                            }
                         }
                     }
                 }
@@ -265,19 +356,39 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
 #pragma unroll
                         for (int g = 0; g < TGT; g++) nexec += gvalid[g];
                     }
+                    if constexpr (A32) {
+                        // partial sums of another aligned source group are still pending: they join the FP64 accumulators first
+                        const int sg = (l0 / 32 + sub) / CONN_A32_GROUPS;
+                        if (pend >= 0 && pend != sg) flush();
+                        pend = sg;
+                        // does the group of 32 sources at hand hold one of the warp's own targets, or is one of its target groups out of reach?
+                        bool special = false;
+#pragma unroll
+                        for (int g = 0; g < TGT; g++) special = special || (CULL && far[g]) || l0 + 32 * sub == slot0 + (wid * TGT + g) * 32;
+                        if (special) {
 #pragma unroll 1
-                    for (int j = 32 * sub; j < 32 * sub + 32; j += CONN_BATCH) batch(j);
+                            for (int j = 32 * sub; j < 32 * sub + 32; j += CONN_BATCH) batch(j, std::true_type());
+                        } else {
+#pragma unroll 1
+                            for (int j = 32 * sub; j < 32 * sub + 32; j += CONN_BATCH) batch(j, std::false_type());
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = 32 * sub; j < 32 * sub + 32; j += CONN_BATCH) batch(j, std::true_type());
+                    }
                 }
             }
             __syncthreads();
             cur = nxt; stage ^= 1;
         }
+        if (pend >= 0) flush();
 #pragma unroll
         for (int g = 0; g < TGT; g++) {
             const int k = kp[g];
             if (k >= 0) {
 #pragma unroll
-                for (int t = 0; t < NYB; t++) if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = acc[g][t];
+                for (int t = 0; t < NYB; t++)
+                    if (32 * w + t < a.ntrans) Sout[(size_t)(32 * w + t) * n + k] = A32 ? sacc[(g * NYB + t) * NTHR] : acc[A32 ? 0 : g][A32 ? 0 : t];
             }
         }
     }

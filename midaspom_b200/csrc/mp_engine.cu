@@ -57,7 +57,7 @@ template <typename R> static int launch_pack_sources(mp_engine *h, int set_mask)
     CK(cudaGetLastError());
     return MP_OK;
 }
-template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_base, int nsets)
+template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_base, int nsets, bool eval)
 {
     Timed tm(h, MP_K_CONN);
     ConnArgs<R> a;
@@ -82,6 +82,14 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     const int shape = h->conn_shape ? h->conn_shape : wide_ctas >= 16LL * h->sm_count ? 1 : wide_ctas >= 4LL * h->sm_count ? 2 : 3;
     const int per_cta = shape == 1 ? 256 : shape == 2 ? 128 : 64;
     dim3 grid((a.k_hi - a.k_lo + per_cta - 1) / per_cta, h->cfg.n_chains, nsets);
+    // Evaluation entry points of the FP32 engines (mp_connectivity, mp_loglik, mp_loglik_host): the year contraction on the FP32
+    // pipe (FFMA2, FP32 partial sums per 32 sources joined in FP64; mp_conn32.cu), accurate to ~1e-7 of every S.  The sampler's
+    // own S keeps the DFMA form below: a weight the y scan later removes must cancel to the last bit even where S then falls
+    // by orders of magnitude.  MP_CONN_ACC32=0 keeps the DFMA form everywhere.
+    if (sizeof(R) == 4 && eval && h->conn_acc32) {
+        h->S_exact = false;
+        return mp_launch_conn32(h, &a, GEOM, ny, shape, cull ? 1 : 0, grid.x, grid.y, grid.z);
+    }
 #define MP_CONN_T(NYB, NT) do { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, NT><<<grid, NT, 0, h->stream>>>(a);      \
                                 else k_conn<R, GEOM, NYB, false, 2, NT><<<grid, NT, 0, h->stream>>>(a); } while (0)
 #define MP_CONN(NYB) do { if (shape == 1) MP_CONN_T(NYB, 128); else if (shape == 2) MP_CONN_T(NYB, 64); else MP_CONN_T(NYB, 32); } while (0)
@@ -104,13 +112,14 @@ static int launch_conn_bounds(mp_engine *h)
     return MP_OK;
 }
 // sets [set_base, set_base + nsets): 0 = resident parameters -> S, 1 = proposal -> S_prop
-template <typename R> static int launch_conn(mp_engine *h, int set_base, int nsets)
+// eval: the call serves an evaluation entry point (FP32 engines may take the FP32 contraction), not the sampler's resident S
+template <typename R> static int launch_conn(mp_engine *h, int set_base, int nsets, bool eval = false)
 {
     if (nsets <= 0) return MP_OK;
     switch (h->geom) {
-    case MP_GEOM_LINEAR: return launch_conn_g<R, MP_GEOM_LINEAR>(h, set_base, nsets);
-    case MP_GEOM_COORDS: return launch_conn_g<R, MP_GEOM_COORDS>(h, set_base, nsets);
-    default: return launch_conn_g<R, MP_GEOM_DENSE>(h, set_base, nsets);
+    case MP_GEOM_LINEAR: return launch_conn_g<R, MP_GEOM_LINEAR>(h, set_base, nsets, eval);
+    case MP_GEOM_COORDS: return launch_conn_g<R, MP_GEOM_COORDS>(h, set_base, nsets, eval);
+    default: return launch_conn_g<R, MP_GEOM_DENSE>(h, set_base, nsets, eval);
     }
 }
 // colonisation log-likelihood partials: set s uses parameters par_s, connectivity S_s, writes partial[s]
@@ -271,20 +280,22 @@ static bool gemm_eligible(const mp_engine *h)
         if (h->par_host[c].alpha != h->par_host[0].alpha || h->par_host[c].b != h->par_host[0].b) return false;
     return true;
 }
-// recompute S (set 0) from the resident y and parameters
+// recompute S (set 0) from the resident y and parameters; allow_gemm: for an evaluation entry point (the FP32 engines may then
+// take the tensor-core path or the FP32 contraction of k_conn, after which the next sweep recomputes the sampler's S)
 template <typename R> static int refresh_S(mp_engine *h, bool allow_gemm = true)
 {
     int rc;
     if ((rc = launch_area_weights<R>(h, 0)) != MP_OK) return rc;
     if (allow_gemm && gemm_eligible(h)) {
         if ((rc = mp_launch_conn_gemm(h, h->par_host[0].alpha)) != MP_OK) return rc;
-        h->S_valid = true; h->last_conn_path = 1;
+        h->S_valid = true; h->S_exact = false; h->last_conn_path = 1;
         return MP_OK;
     }
     h->last_conn_path = 0;
     if ((rc = launch_pack_sources<R>(h, 1)) != MP_OK) return rc;
     if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
-    const int rc2 = launch_conn<R>(h, 0, 1);
+    h->S_exact = true;                                   // launch_conn clears it when it takes the FP32 contraction
+    const int rc2 = launch_conn<R>(h, 0, 1, allow_gemm);
     if (rc2 == MP_OK) h->S_valid = true;
     return rc2;
 }
@@ -325,7 +336,7 @@ template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out
     }
     // The resident S is maintained by exact rank-1 updates; the FP32 engine recomputes it from scratch only
     // every MP_REFRESH_EVERY sweeps (the FP64 parity engine every sweep, like the CPU twin).
-    const bool refresh = is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0 || !h->S_valid;
+    const bool refresh = is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0 || !h->S_valid || !h->S_exact;
     if (refresh || do_ab) if ((rc = launch_pack_sources<R>(h, (refresh ? 1 : 0) | (do_ab ? 2 : 0))) != MP_OK) return rc;
     if ((rc = launch_conn_bounds(h)) != MP_OK) return rc;
     if (sharded) {   // other ranks fill the other target columns: start from zeros so that a sum over ranks assembles S
@@ -333,7 +344,7 @@ template <typename R> static int phase_propose_conn(mp_engine *h, int *flags_out
         if (do_ab) CK(cudaMemsetAsync(h->d_S[1], 0, nC(h) * ycells(h) * 8, h->stream));
     }
     if ((rc = launch_conn<R>(h, refresh ? 0 : 1, (refresh ? 1 : 0) + (do_ab ? 1 : 0))) != MP_OK) return rc;
-    h->S_valid = true;
+    h->S_valid = true; h->S_exact = true;
     if (flags_out) *flags_out = (refresh ? 1 : 0) | (do_ab ? 2 : 0);
     return MP_OK;
 }
@@ -496,6 +507,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     if (const char *env = getenv("MP_CONN_CULL")) h->conn_cull = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_GEMM")) h->use_gemm = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_GEMM_MIN_N")) { const int v = atoi(env); if (v >= 1) h->gemm_min_n = v; }
+    if (const char *env = getenv("MP_CONN_ACC32")) h->conn_acc32 = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 3) h->conn_shape = v; }
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
@@ -1071,7 +1083,7 @@ int mp_sweep(mp_engine *h, int nsweeps)
         // memory), so it is captured once per kind -- without / with the refresh of the resident S -- and replayed as a CUDA
         // graph: on small landscapes the sweep is launch-bound.  The first sweep of a kind runs eagerly (lazy allocations).
         const bool whole = h->conn_hi < 0 && h->task_first == 0 && h->task_stride == 1;
-        if (h->use_graph && !h->timing && h->S_valid && whole) {
+        if (h->use_graph && !h->timing && h->S_valid && h->S_exact && whole) {
             const int v = (is64(h) || h->refresh_every <= 1 || (h->sweep % (uint32_t)h->refresh_every) == 0) ? 1 : 0;
             if (!h->gexec[v] && h->gwarm[v]) {
                 const uint32_t sweep0 = h->sweep; const int ndraws0 = h->ndraws;

@@ -57,6 +57,8 @@ struct mp_engine {
     int sm_count = 148;
     int refresh_every = 16;          // FP32 engine: sweeps between from-scratch recomputations of the resident S
     bool S_valid = false;            // resident S corresponds to the resident (y, alpha, b)
+    bool S_exact = true;             // ... and was accumulated in FP64 (false after an evaluation call that took the tensor-core path or the
+                                     // FP32 contraction: the next sweep recomputes it before the y scan applies rank-1 updates to it)
     int task_first = 0, task_stride = 1;   // (chain, year) tasks of the y sweep run by this engine (year sharding)
     int conn_lo = 0, conn_hi = -1;        // target patches of k_conn run by this engine (patch sharding); hi < 0 = all
     void *d_tile_box = nullptr;                // float4 {xmin, xmax, ymin, ymax} per group of 32 scan-order slots (culled k_conn)
@@ -68,6 +70,7 @@ struct mp_engine {
     bool par_host_valid = false;               // ... still what the device holds (the sampler changes them on the device)
     int use_gemm = 1, gemm_min_n = 1024;       // tensor-core connectivity for chains sharing (alpha, b): MP_CONN_GEMM=0 disables, MP_CONN_GEMM_MIN_N
     int last_conn_path = 0;                    // 0: k_conn, 1: k_conn_gemm (mp_get_conn_path)
+    int conn_acc32 = 1;   // FP32 engines, evaluation entry points: year contraction of k_conn on the FP32 pipe (mp_conn32.cu); MP_CONN_ACC32=0 keeps the DFMA form
     int conn_shape = 0;                        // CTA shape of k_conn: 0 choose, 1 = 128 threads x 2 targets, 2 = 64 x 2, 3 = 32 x 2 (MP_CONN_SHAPE)
     unsigned long long *d_work = nullptr;      // MP_CNT_* work counters (mp_get_work_counters)
     int *d_task_order = nullptr;               // scan tasks of this engine, longest first (k_order_tasks)
@@ -176,5 +179,7 @@ int mp_launch_sweep_fast_dense(mp_engine *h, int cs, int tpt);
 // culled scan: nclusters whole (chain, year) tasks (btasks == nullptr) or block tasks (mp::BlockTask array on the device)
 int mp_launch_sweep_cull_linear(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks);
 int mp_launch_sweep_cull_coords(mp_engine *h, int cs, int tpt, int nl_max, int nclusters, const void *btasks);
+// k_conn of the FP32 engines with the year contraction on the FP32 pipe (mp_conn32.cu); args: the launch's mp::ConnArgs<float>
+int mp_launch_conn32(mp_engine *h, const void *args, int geom, int ny, int shape, int cull, unsigned gx, unsigned gy, unsigned gz);
 // tensor-core connectivity of every chain with one (alpha, b) (mp_conn_gemm.cu)
 int mp_launch_conn_gemm(mp_engine *h, double alpha);

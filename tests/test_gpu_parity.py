@@ -705,7 +705,8 @@ def test_full_size_properties_cfg3(monkeypatch):
         Sab = eng.connectivity()
         eng.set_state(np.stack([z, z]), np.stack([y, np.zeros_like(y)]))
         Sy = eng.connectivity()
-        rel_close(Sab[0] + Sab[1], Sy[0], 1e-12, floor=1e-9)   # linearity: FP64 accumulation of identical weights
+        # linearity: identical weights, FP32 partial sums per 32 sources (k_conn's FP32 contraction: <= ~1.5e-7 each) joined in FP64
+        rel_close(Sab[0] + Sab[1], Sy[0], 1e-6, floor=1e-9)
         assert (Sy[1] == 0).all()
         t, k = 7, int(np.flatnonzero(z[7] & z[8])[5])
         delta32 = eng.flip_delta(0, t, k)
