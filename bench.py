@@ -466,6 +466,9 @@ def run_ours(args, rank, local_rank, world):
                     higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f32", data="synthetic",
                     config=workload_config(args, wl, chains_total, cpg, world),
                     run=dict(chains_per_gpu=cpg, weights="evaluated on the fly from the coordinates",
+                             connectivity=dict(sampler="k_conn, year contraction in FP64 (DFMA): rank-1 removals by the y scan cancel exactly",
+                                               likelihood_calls="k_conn, year contraction in FP32 (FFMA2, partial sums per 32 sources joined in FP64); "
+                                                                "k_conn_gemm (tcgen05) when every chain holds the same (alpha, b)"),
                              sampled=["e", "c", "alpha", "b"] + (["p"] if wl["detect"] else []) + (["Ksrc", "dsrc"] if "src_unit" in wl else ["K"] if "era" in wl else []),
                              parallelism=f"chains x{world}", scan=scan_geo),
                     clocks=clk.summary(),

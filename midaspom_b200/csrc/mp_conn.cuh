@@ -205,13 +205,29 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
         for (int g = 0; g < TGT; g++) { gbox[g] = a.box32[min(w0 + g, gend - 1)]; thr[g] = thr_of(min(w0 + g, gend - 1)); }   // the warp's g-th group
     }
     const int ntile = (n + NTHR - 1) / NTHR;
-    // first tile >= i with a (target, source) pair within reach of the CTA (CTA-uniform)
+    // first tile >= i with a (target, source) pair within reach of the CTA (CTA-uniform).  The tiles are tested 32 at a time, one
+    // per lane (every warp does the same test and holds the same mask): one round of box loads per 32 tiles instead of a
+    // dependent load per tile -- on wide landscapes most tiles are out of reach (97 % at cfg5) and the scan over them is latency.
+    uint32_t tmask = 0u;                                             // in-reach tiles of the chunk of 32 tiles at hand
+    int tchunk = -1;
     auto next_tile = [&](int i) {
         if (!CULL) return i;
-        for (; i < ntile; i++) {
-            float4 sb = a.box32[i * (NTHR / 32)];
-            for (int u = 1; u < NTHR / 32; u++) if (i * NTHR + 32 * u < n) sb = box_union(sb, a.box32[i * (NTHR / 32) + u]);
-            if (!(reach_log2(tbox, sb) < thr_cta)) break;
+        while (i < ntile) {
+            const int ch = i >> 5;
+            if (ch != tchunk) {
+                const int ti = ch * 32 + lane;
+                bool in = false;
+                if (ti < ntile) {
+                    float4 sb = a.box32[ti * (NTHR / 32)];
+                    for (int u = 1; u < NTHR / 32; u++) if (ti * NTHR + 32 * u < n) sb = box_union(sb, a.box32[ti * (NTHR / 32) + u]);
+                    in = !(reach_log2(tbox, sb) < thr_cta);
+                }
+                tmask = __ballot_sync(0xffffffffu, in);
+                tchunk = ch;
+            }
+            const uint32_t m = tmask >> (i & 31);
+            if (m) return i + __ffs((int)m) - 1;
+            i = (ch + 1) * 32;
         }
         return i;
     };
@@ -340,6 +356,12 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
                 }
             };
             if (warp_live) {
+                float4 sbox[NTHR / 32];                              // boxes of the tile's source groups: independent loads, one latency
+                if (CULL) {
+#pragma unroll
+                    for (int sub = 0; sub < NTHR / 32; sub++) sbox[sub] = a.box32[min(l0 / 32 + sub, (n + 31) / 32 - 1)];
+                }
+#pragma unroll
                 for (int sub = 0; sub < NTHR / 32; sub++) {          // warp-uniform: 32 sources against the warp's TGT target groups
                     if (l0 + 32 * sub >= n) continue;
                     if (CULL) {
@@ -347,7 +369,7 @@ __global__ void __launch_bounds__(NTHR) k_conn(ConnArgs<R> a)
                         uint32_t nlive = 0;
 #pragma unroll
                         for (int g = 0; g < TGT; g++) {
-                            far[g] = reach_log2(gbox[g], a.box32[l0 / 32 + sub]) < thr[g];
+                            far[g] = reach_log2(gbox[g], sbox[sub]) < thr[g];
                             all_far = all_far && far[g]; nlive += !far[g] && gvalid[g];
                         }
                         if (all_far) continue;

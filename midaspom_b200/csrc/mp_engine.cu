@@ -76,11 +76,14 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     constexpr bool CAN_CULL = sizeof(R) == 4 && GEOM != MP_GEOM_DENSE;
     const bool cull = CAN_CULL && h->conn_cull && h->have_boxes;
     // CTA shape: 128 threads x 2 targets; with few CTAs per SM, 64 or 32 threads x 2 targets (2x / 4x the CTAs) balance the
-    // unequal (culled) work better.  MP_CONN_SHAPE=1|2|3 forces a shape.
+    // unequal (culled) work better, and the FP32 engines go on to 32 threads x 1 target (8x the CTAs, 96 registers: cfg3 with
+    // 8 chains 1.41 -> 1.25 ms per launch; no difference at cfg5).  Every shape gives bit-identical sums.  MP_CONN_SHAPE=1|2|3|4
+    // forces a shape.
     const long long wide_ctas = (long long)((a.k_hi - a.k_lo + 255) / 256) * h->cfg.n_chains * nsets;
-    // shape 1: 128 threads, 2: 64 threads, 3: 32 threads (2 targets per thread each)
-    const int shape = h->conn_shape ? h->conn_shape : wide_ctas >= 16LL * h->sm_count ? 1 : wide_ctas >= 4LL * h->sm_count ? 2 : 3;
-    const int per_cta = shape == 1 ? 256 : shape == 2 ? 128 : 64;
+    // shape 1: 128 threads, 2: 64 threads, 3: 32 threads (2 targets per thread each), 4: 32 threads x 1 target (FP32 engines)
+    int shape = h->conn_shape ? h->conn_shape : wide_ctas >= 16LL * h->sm_count ? 1 : wide_ctas >= 4LL * h->sm_count ? 2 : 4;
+    if (shape == 4 && (sizeof(R) != 4 || (eval && h->conn_acc32))) shape = 3;
+    const int per_cta = shape == 1 ? 256 : shape == 2 ? 128 : shape == 3 ? 64 : 32;
     dim3 grid((a.k_hi - a.k_lo + per_cta - 1) / per_cta, h->cfg.n_chains, nsets);
     // Evaluation entry points of the FP32 engines (mp_connectivity, mp_loglik, mp_loglik_host): the year contraction on the FP32
     // pipe (FFMA2, FP32 partial sums per 32 sources joined in FP64; mp_conn32.cu), accurate to ~1e-7 of every S.  The sampler's
@@ -92,10 +95,14 @@ template <typename R, int GEOM> static int launch_conn_g(mp_engine *h, int set_b
     }
 #define MP_CONN_T(NYB, NT) do { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 2, NT><<<grid, NT, 0, h->stream>>>(a);      \
                                 else k_conn<R, GEOM, NYB, false, 2, NT><<<grid, NT, 0, h->stream>>>(a); } while (0)
-#define MP_CONN(NYB) do { if (shape == 1) MP_CONN_T(NYB, 128); else if (shape == 2) MP_CONN_T(NYB, 64); else MP_CONN_T(NYB, 32); } while (0)
+#define MP_CONN_ONE(NYB) do { if constexpr (sizeof(R) == 4) { if (cull) k_conn<R, GEOM, NYB, CAN_CULL, 1, 32><<<grid, 32, 0, h->stream>>>(a);   \
+                                                              else k_conn<R, GEOM, NYB, false, 1, 32><<<grid, 32, 0, h->stream>>>(a); } } while (0)
+#define MP_CONN(NYB) do { if (shape == 1) MP_CONN_T(NYB, 128); else if (shape == 2) MP_CONN_T(NYB, 64); else if (shape == 3) MP_CONN_T(NYB, 32); \
+                          else MP_CONN_ONE(NYB); } while (0)
     if (ny <= 4) MP_CONN(4); else if (ny <= 8) MP_CONN(8); else if (ny <= 12) MP_CONN(12); else if (ny <= 16) MP_CONN(16);
     else if (ny <= 20) MP_CONN(20); else if (ny <= 24) MP_CONN(24); else if (ny <= 28) MP_CONN(28); else MP_CONN(32);
 #undef MP_CONN
+#undef MP_CONN_ONE
 #undef MP_CONN_T
     CK(cudaGetLastError());
     return MP_OK;
@@ -508,7 +515,7 @@ int mp_create(const mp_config *cfg, mp_engine **out)
     if (const char *env = getenv("MP_CONN_GEMM")) h->use_gemm = atoi(env) != 0;
     if (const char *env = getenv("MP_CONN_GEMM_MIN_N")) { const int v = atoi(env); if (v >= 1) h->gemm_min_n = v; }
     if (const char *env = getenv("MP_CONN_ACC32")) h->conn_acc32 = atoi(env) != 0;
-    if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 3) h->conn_shape = v; }
+    if (const char *env = getenv("MP_CONN_SHAPE")) { const int v = atoi(env); if (v >= 0 && v <= 4) h->conn_shape = v; }
     if (const char *env = getenv("MP_REFRESH_EVERY")) { const int v = atoi(env); if (v >= 1) h->refresh_every = v; }
     if (const char *env = getenv("MP_FAST_CS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->fast_cs = v; }
     if (const char *env = getenv("MP_FAST_TPT")) { const int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096 || v == 8192) h->fast_tpt = v; }
