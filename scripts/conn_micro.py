@@ -2,7 +2,7 @@
 """Micro-benchmark of the connectivity kernels on the cfg3 landscape: ms per mp_connectivity call (engine timing, CUDA events)
 for k_conn (per-chain parameters) and, when every chain shares (alpha, b), the tensor-core path.
     python scripts/conn_micro.py [chains] [reps] [gemm: 0|1]"""
-import sys, json
+import os, sys, json
 from pathlib import Path
 import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -28,5 +28,5 @@ for _ in range(reps):
     eng.connectivity(fetch=False)
 ms, n = eng.get_timing(reset=True)
 w = eng.work_counters()
-print(json.dumps(dict(chains=chains, path=eng.conn_path(), conn_ms_per_call=ms["conn"] / max(1, n["conn"]), small_ms_per_call=ms["small"] / reps,
+print(json.dumps(dict(chains=chains, path=eng.conn_path(), contraction="fp64" if os.environ.get("MP_CONN_ACC32", "1") == "0" else "fp32", conn_ms_per_call=ms["conn"] / max(1, n["conn"]), small_ms_per_call=ms["small"] / reps,
                       executed_fraction=(w["conn_exec"] / max(1, w["conn_total"])) if w["conn_total"] else None, gemm_tiles=w["gemm_tiles"])))
