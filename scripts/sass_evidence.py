@@ -35,3 +35,16 @@ for obj in ("mp_conn_gemm.o", "mp_engine.o"):
             if kk == k and base.startswith(("UTC", "UTMA", "UBLKCP", "LDTM")):
                 print(ln[:150])
         print("```\n")
+
+# the FP32 year contraction of k_conn (mp_conn32.o): packed FP32 FMAs, two years per instruction
+sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2mp6k_connIfLi1ELi20ELb1ELi2ELi128ELb1EEEvNS_8ConnArgsIT_EE", str(OBJ / "mp_conn32.o")], capture_output=True, text=True).stdout
+ops = collections.Counter(re.sub(r"\..*", "", m.group(1)) for m in re.finditer(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", sass, re.M))
+first = next((ln.strip() for ln in sass.splitlines() if "FFMA2" in ln), "")
+print("## mp_conn32.o\n")
+print("### `void mp::k_conn<float, 1, 20, true, 2, 128, true>` (cfg3: coordinates, 19 years, culled, 128 threads x 2 targets, FP32 contraction)\n")
+print("| mnemonic | static count |\n|---|---|")
+for o in ("FFMA2", "FFMA", "DFMA", "DADD", "F2F", "MUFU", "UBLKCP", "LDS", "STS"):
+    print(f"| {o} | {ops.get(o, 0)} |")
+print("\n`FFMA2` = fma.rn.f32x2 (the weight as a broadcast `.F32` operand, two years of the 0/1 table as the `.F32x2` operand); no DFMA: the FP64 work is the join of the partial sums (`F2F` + `DADD`).\n\n```")
+print(first[:150])
+print("```")
