@@ -123,7 +123,8 @@ int mp_set_scales(mp_engine *h, const double *lsig /* C*MP_NLSIG */);
 int mp_get_scales(mp_engine *h, double *lsig);
 
 /* ---- likelihood ---- */
-/* recompute S from the current y and parameters; S_out (host, C*(T-1)*N, nullable) */
+/* recompute S from the current y and parameters; S_out (host, C*(T-1)*N, nullable).  FP64 engines: 1e-9 path.  FP32 engines: the
+ * evaluation form of k_conn (or the tensor-core path, see mp_get_conn_path), inside the FP32 path's 1e-5 */
 int mp_connectivity(mp_engine *h, double *S_out);
 int mp_get_connectivity(mp_engine *h, double *S_out);   /* copy of the resident S (no recompute) */
 /* complete-data log-likelihood per chain (recomputes S); parts: C*MP_NPART, nullable */
@@ -228,7 +229,9 @@ int mp_get_timing(mp_engine *h, double *ms, int64_t *launches, int reset);
 enum { MP_CNT_SCAN_TRIPS = 0, MP_CNT_SCAN_EXEC = 1, MP_CNT_SCAN_RETIRED = 2, MP_CNT_SCAN_COMMIT = 3, MP_CNT_SCAN_DENSE = 4,
        MP_CNT_CONN_EXEC = 5, MP_CNT_CONN_TOTAL = 6, MP_CNT_GEMM_TILES = 7, MP_CNT_SCAN_BLOCKS = 8, MP_CNT_N = 9 };
 int mp_get_work_counters(mp_engine *h, uint64_t *out /* MP_CNT_N */, int reset);
-/* which kernel evaluated the connectivity last: 0 = k_conn (per-chain parameters, FP64 accumulation), 1 = the tensor-core
+/* which kernel evaluated the connectivity last: 0 = k_conn (per-chain parameters; the sampler's own S with the year contraction
+ * in FP64, the evaluation calls mp_connectivity / mp_loglik / mp_loglik_host of an FP32 engine with FP32 partial sums per 32
+ * sources joined in FP64, ~1e-7 of every S -- the sweep after such a call recomputes the resident S), 1 = the tensor-core
  * contraction k_conn_gemm (FP32 engines; taken by mp_connectivity / mp_loglik / mp_loglik_host when every chain holds the
  * same alpha and b as uploaded by mp_set_params, the matrix form c*M%*%pti of Rscript/simuls_traj.R:16,203,214) */
 int mp_get_conn_path(mp_engine *h);
