@@ -736,3 +736,34 @@ def test_full_size_properties_cfg3(monkeypatch):
             assert (zg[c][obs == 1] == 1).all() and (zg[c][obs == 0] == 0).all()
         d = eng.get_draws()
         assert np.isfinite(d[:, :, 5]).all()
+
+
+@pytest.mark.parametrize("geom,n", [(O.GEOM_COORDS, 700), (O.GEOM_LINEAR, 600), (O.GEOM_COORDS, 4100)])
+def test_evaluation_calls_between_sweeps_leave_the_sampler_exact(geom, n):
+    """mp_loglik / mp_connectivity of an FP32 engine take the FP32 year contraction of k_conn (partial sums per 32 sources,
+    ~1e-7 of S) and leave that S resident; the sweep that follows must recompute the resident S with the FP64 contraction
+    before the y scan applies rank-1 updates to it -- also when sweeps are replayed as CUDA graphs and the call falls between
+    two refreshes.  Checked where it shows: on the linear landscape isolated targets lose orders of magnitude of S when their
+    neighbours are removed, and an inexact start would leave a relative error of order one there."""
+    rng = np.random.default_rng(900 + n)
+    T, C = 6, 3
+    spec, z, y = random_landscape(rng, n, T, geom, occ=0.5, miss=0.05)
+    par = pdict(e=0.35, c=0.02 if geom != O.GEOM_LINEAR else 0.2, alpha=1 / 400, b=0.5)
+    sc = mb.engine.sampler_config(sample_e=1, sample_c=1, sample_alpha=1, sample_b=1, alpha_min=1e-4, alpha_max=1e-1, c_max=0.5, n_adapt=2)
+    with make_engine(spec, n_chains=C, precision=mb.FP32, seed=5, max_draws=64) as eng:
+        eng.set_params([par] * C)
+        eng.set_state(np.stack([z] * C), np.stack([y] * C))
+        eng.init_chains(sc, disperse=False)
+        eng.sweep(20)                                             # both kinds of sweep have been captured by now
+        ll_a, _ = eng.loglik()                                    # FP32 contraction; the resident S is now the evaluation's
+        eng.sweep(3)                                              # sweeps 20..22: none of them is a scheduled refresh
+        zz, yy = eng.get_state()
+        S_inc = eng.get_connectivity()
+        ll_b, _ = eng.loglik()
+        S_new = eng.get_connectivity()
+        rel_close(S_inc, S_new, 1e-6, floor=1e-9)                 # rank-1 bookkeeping on top of an exact start
+        assert np.isfinite(ll_a).all() and np.isfinite(ll_b).all()
+        assert ((yy <= zz[:, :-1]) & (yy <= zz[:, 1:])).all()
+        assert eng.num_draws() == 23
+        d = eng.get_draws()
+        assert np.isfinite(d[:, :, 5]).all()
