@@ -10,7 +10,8 @@
 //                  dispersal weight is evaluated once per (target, source) pair and contracted over the years with
 //                  acc[t] = fma(w, y01[t], acc[t]) (exactly acc[t] + w or acc[t]).  FP64 accumulation in both precisions so
 //                  that later rank-1 removals of the same FP32 weight by the y scan cancel exactly.
-//                  A32 variant (FP32 engines, mp_conn32.cu): the year contraction of each group of 32 sources runs on the
+//                  A32 variant (mp_conn32.cu; the evaluation entry points of the FP32 engines -- the sampler's resident S keeps
+//                  the FP64 form, see launch_conn_g in mp_engine.cu): the year contraction of each group of 32 sources runs on the
 //                  FP32 pipe as packed FFMA2 (fma.rn.f32x2: two years per instruction) into FP32 partial sums, which join
 //                  the FP64 accumulators (in shared memory, one column per thread) after every group of 32 sources -- half
 //                  the pipe time of the DFMA form and a third of its issue slots.  A partial sum rounds at 2^-24 over at most
