@@ -557,6 +557,14 @@ def roofline(workload, wl, cpg, ncand, kms, klaunch, work, geo, probe, hbm_peak,
                         frac=conn_pairs * 2.0 / t_conn * 1e-9 / peak, pairs_executed_per_launch=conn_pairs,
                         pairs_dense_per_launch=conn_total, share_of_step=kms["conn"] / max(split_total_ms, 1e-9),
                         counters=c_counters, traffic=(c_traffic or {}).get("bytes_per_launch"), traffic_detail=c_traffic)
+    # the sampler's k_conn contracts every executed pair over the years in FP64: the FP64 pipe, not the MUFU, bounds it
+    nyb = min(32, (T - 1 + 3) // 4 * 4)                                   # year accumulators per target and pass (k_conn's NYB)
+    fp64_peak = float(probe.get("dadd_gops", 0.0)) if probe else 0.0
+    if fp64_peak > 0:
+        dfma = conn_pairs * nyb                                           # conn_exec counts every pass (32 years each) over the sources
+        roof["conn"]["fp64"] = dict(achieved=dfma / t_conn * 1e-9, peak=fp64_peak, unit="Gop/s (DFMA)", frac=dfma / t_conn * 1e-9 / fp64_peak,
+                                    dfma_per_pair=nyb, note="executed (target, source) pairs x year accumulators / launch time / FP64 peak "
+                                                            "(mp_probe_peaks, builder-measured); compare with counters.pipe_fp64_pct")
     return roof
 
 

@@ -70,3 +70,38 @@ def test_synthetic_workloads_are_deterministic_and_feasible():
     assert (np.diag(W) == 0).all()
     i, j = 3, 17
     assert np.isclose(W[i, j], np.exp(-np.hypot(a["px"][i] - a["px"][j], a["py"][i] - a["py"][j]) / 400) * a["area"][i] ** 0.5)
+
+
+def test_bench_roofline_from_work_counters():
+    """bench.py's roofline block on the numbers of a real cfg3 line (profiles/r02_bench_cfg3.json): fractions of the MUFU peak
+    (scan) and of the FP64 peak (k_conn) come from executed work and stay below 1; the culled and the unculled scan both work."""
+    import importlib.util
+    import json
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("bench_mod", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = dict(n=10000, T=20)
+    kms = dict(conn=149.574, col=6.58, sweep_y=1197.05, sweep_z=6.65, small=18.79, sim=0.0)
+    klaunch = dict(conn=20, col=60, sweep_y=20, sweep_z=20, small=280, sim=0)
+    # engine counters of 20 sweeps of 64 chains (groups of 32 targets; tiles of 32 x 32 pairs)
+    work = dict(scan_trips=78_600_000, scan_exec=12_600_000_000, scan_retired=11_000_000_000, scan_commit=4_300_000_000, scan_dense=0,
+                conn_exec=55_000_000, conn_total=137_900_000, gemm_tiles=0, scan_blocks=0)
+    geo = dict(threads_per_task=512, cluster=1, candidates_per_trip=2, culled=True, blocks=False)
+    probe = dict(mufu_gops=4613.8, ffma_gfma=31600.0, dadd_gops=18000.0, copy_gbs=6400.0)
+    roof = bench.roofline("cfg3", wl, 64, 102752.0, kms, klaunch, work, geo, probe, 6650.0, True, sum(kms.values()))
+    assert roof["kernel"] == "k_sweep_y_cull" and 0.05 < roof["frac"] < 1.0 and roof["executed"]["frac"] >= roof["frac"]
+    conn = roof["conn"]
+    assert 0.0 < conn["frac"] < 1.0
+    assert conn["fp64"]["dfma_per_pair"] == 20 and 0.1 < conn["fp64"]["frac"] < 1.0
+    assert abs(conn["fp64"]["frac"] - conn["pairs_executed_per_launch"] * 20 / (conn["ms_per_launch"] * 1e-3) * 1e-9 / 18000.0) < 1e-12
+    json.dumps(roof)                                              # the block goes into the bench's JSON line
+    # unculled scan (cfg2: k_sweep_y_fast), more than 32 years: 32 accumulators per pass
+    geo2 = dict(threads_per_task=256, cluster=1, candidates_per_trip=1, culled=False, blocks=False)
+    work2 = dict(work, scan_dense=3_000_000_000, scan_exec=0, scan_retired=0, scan_commit=0, scan_trips=0)
+    roof2 = bench.roofline("cfg2", dict(n=1000, T=41), 8, 3000.0, kms, klaunch, work2, geo2, probe, 6650.0, False, sum(kms.values()))
+    assert roof2["kernel"] == "k_sweep_y_fast" and roof2["conn"]["fp64"]["dfma_per_pair"] == 32
+    # no probe figure for the FP64 peak: the block is simply absent
+    roof3 = bench.roofline("cfg3", wl, 64, 102752.0, kms, klaunch, work, geo, dict(probe, dadd_gops=0.0), 6650.0, True, sum(kms.values()))
+    assert "fp64" not in roof3["conn"]
